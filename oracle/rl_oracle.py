@@ -1,0 +1,557 @@
+"""CPU oracle for the actor-learner hot path (advantages, PPO/GRPO loss, policy, optimiser).
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import it.  Nothing under `rlinf_b200/` imports it: the product
+path is the CUDA library and fails loudly when that library is missing.
+
+It is a restatement, in plain fp32 PyTorch-on-CPU arithmetic (the arithmetic the
+reference itself uses: the reference is 100 % Python/PyTorch and its embodied
+path runs these functions on CPU tensors), of the reference algorithm
+(RLinf v0.4.0).  Each function cites the reference file:line it follows.
+
+Parity pinning: the reference's own tests hold NO golden vector for this path
+ -> "parity unpinned by the reference's tests".  The oracle
+is instead pinned against the reference ITSELF, executed unmodified in the
+build container (`tests/golden/make_golden.py` -> `tests/golden/*.npz`,
+checked by `tests/test_oracle_golden.py`).
+
+Third-party arithmetic on the path: torch==2.11.0 (pyproject.toml:151 of the
+reference; same version here) supplies `torch.optim.AdamW`,
+`torch.nn.utils.clip_grad_norm_`, `torch.randperm` (CPU mt19937) and
+`torch.distributions.Normal`; the oracle calls the same library routines.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+# --------------------------------------------------------------------------
+# masks, reductions
+# --------------------------------------------------------------------------
+
+
+def loss_mask_from_dones(dones: torch.Tensor):
+    """rlinf/utils/metric_utils.py:516-537 (compute_loss_mask).
+
+    dones: bool [nc+1, B, C].  Step-major flatten, keep the last nc*C+1 rows,
+    a step is valid while no done has been seen in rows [0..t]; drop last row.
+    Returns mask bool [nc, B, C] and mask_sum int64 [nc, B, C] (per-env count).
+    """
+    ncp1, bsz, csz = dones.shape
+    nc = ncp1 - 1
+    flat = dones.permute(0, 2, 1).reshape(ncp1 * csz, bsz)[-(nc * csz + 1):]
+    seen = torch.cumsum(flat.to(torch.int64), dim=0)
+    valid = (seen == 0)[:-1]
+    mask = valid.reshape(nc, csz, bsz).permute(0, 2, 1)
+    per_env = mask.sum(dim=(0, 2), keepdim=True)
+    return mask, per_env.expand_as(mask)
+
+
+def masked_mean(values: torch.Tensor, mask: Optional[torch.Tensor]):
+    """rlinf/utils/utils.py:323-330: None -> mean; all-False -> sum(v*m) (=0)."""
+    if mask is None:
+        return values.mean()
+    if bool((~mask).all()):
+        return (values * mask).sum()
+    return (values * mask).sum() / mask.sum()
+
+
+def masked_mean_ratio(values, mask, ratio):
+    """rlinf/utils/utils.py:352-356: divides by the TOTAL element count."""
+    return (values / ratio * mask).mean()
+
+
+def huber(err: torch.Tensor, delta: float):
+    """rlinf/algorithms/utils.py:20-23."""
+    a = err.abs()
+    return torch.where(a < delta, 0.5 * err**2, delta * (a - 0.5 * delta))
+
+
+def kl_penalty(logprob, ref_logprob, kind: str):
+    """rlinf/algorithms/utils.py:26-64."""
+    if kind in ("kl", "k1"):
+        return logprob - ref_logprob
+    if kind == "abs":
+        return (logprob - ref_logprob).abs()
+    if kind in ("mse", "k2"):
+        return 0.5 * (logprob - ref_logprob).square()
+    if kind in ("low_var_kl", "k3"):
+        d = torch.clamp(ref_logprob - logprob, min=-20, max=20)
+        return torch.clamp(torch.exp(d) - d - 1, min=-10, max=10)
+    raise NotImplementedError(kind)
+
+
+def normalize_valid(x: torch.Tensor, mask: Optional[torch.Tensor]):
+    """rlinf/algorithms/utils.py:397-404 (safe_normalize): unbiased std, eps on std."""
+    sel = x[mask] if mask is not None else x.reshape(-1)
+    if sel.numel() > 0:
+        x = (x - sel.mean()) / (sel.std() + 1e-5)
+    return x
+
+
+# --------------------------------------------------------------------------
+# advantages
+# --------------------------------------------------------------------------
+
+
+def chunks_to_steps(rewards, dones, values=None, loss_mask=None, loss_mask_sum=None,
+                    reward_type="action_level", need_values=True):
+    """rlinf/algorithms/utils.py:67-131 (preprocess_embodied_advantages_inputs).
+
+    [nc,B,C] -> [T=nc*C, B]; dones/values [(nc+1),B,C] -> last/first T+1 rows.
+    """
+    if reward_type == "chunk_level":
+        rewards = rewards.sum(dim=-1, keepdim=True)
+        dones = dones.max(dim=-1, keepdim=True)[0]
+        if loss_mask is not None:
+            loss_mask = loss_mask.max(dim=-1, keepdim=True)[0]
+        if loss_mask_sum is not None:
+            loss_mask_sum = loss_mask_sum.max(dim=-1, keepdim=True)[0]
+    nc, bsz, csz = rewards.shape
+    n_steps = nc * csz
+    r = rewards.transpose(1, 2).reshape(n_steps, bsz)
+    m = loss_mask.transpose(1, 2).reshape(n_steps, bsz) if loss_mask is not None else None
+    d = dones.transpose(1, 2).reshape((nc + 1) * csz, bsz)[-(n_steps + 1):]
+    v = None
+    if need_values and values is not None:
+        v = values.transpose(1, 2).reshape((nc + 1) * csz, bsz)[: n_steps + 1]
+    return dict(rewards=r, dones=d, values=v, loss_mask=m, loss_mask_sum=loss_mask_sum,
+                num_chunk=nc, chunk_size=csz, batch_size=bsz, n_steps=n_steps)
+
+
+def steps_to_chunks(x, num_chunk, chunk_size):
+    """rlinf/algorithms/utils.py:155-174."""
+    return x.reshape(num_chunk, chunk_size, -1).transpose(1, 2)
+
+
+def gae(rewards, values=None, dones=None, gamma=1.0, gae_lambda=1.0, loss_mask=None,
+        normalize_advantages=True, normalize_returns=False):
+    """rlinf/algorithms/advantages.py:24-86.  [T,B] tensors, reverse recurrence.
+
+    Op order is kept exactly (each op rounds to fp32 separately):
+      nd = ~done[t+1]; delta = r[t] + gamma*V[t+1]*nd - V[t]
+      g = delta + (gamma*lambda)*nd*g ; ret[t] = g + V[t]; adv = ret - V[:-1]
+    """
+    n_steps = rewards.shape[0]
+    returns = torch.zeros_like(rewards)
+    critic_free = values is None
+    if critic_free:
+        gamma, gae_lambda = 1, 1
+    g = 0
+    for t in range(n_steps - 1, -1, -1):
+        nd = ~dones[t + 1]
+        delta = rewards[t] if critic_free else rewards[t] + gamma * values[t + 1] * nd - values[t]
+        g = delta + gamma * gae_lambda * nd * g
+        returns[t] = g if critic_free else g + values[t]
+    adv = returns if critic_free else returns - values[:-1]
+    if normalize_advantages:
+        adv = normalize_valid(adv, loss_mask)
+    if normalize_returns:
+        returns = normalize_valid(returns, loss_mask)
+    return adv, returns
+
+
+def first_episode_scores(rewards, dones):
+    """rlinf/algorithms/utils.py:134-152 (calculate_scores): reverse accumulation
+    that is reset by every done -> return of the FIRST episode of each env."""
+    n_steps, bsz = rewards.shape
+    s = torch.zeros(bsz)
+    for t in range(n_steps - 1, -1, -1):
+        s = s * ~dones[t + 1]
+        s += rewards[t]
+    return s
+
+
+def grpo_group_advantages(scores, loss_mask, group_size):
+    """rlinf/algorithms/advantages.py:89-121: unbiased group std, eps 1e-6 on std,
+    broadcast over T through the (bool) loss mask."""
+    grp = scores.reshape(-1, group_size)
+    a = (grp - grp.mean(dim=-1, keepdim=True)) / (grp.std(dim=-1, keepdim=True) + 1e-6)
+    return (torch.zeros_like(loss_mask) + a.reshape(1, -1)) * loss_mask
+
+
+def adv_and_returns_embodied(adv_type, rewards, dones, values=None, loss_mask=None,
+                             loss_mask_sum=None, gamma=1.0, gae_lambda=1.0, group_size=8,
+                             reward_type="action_level", **kw):
+    """rlinf/algorithms/registry.py:95-118 (embodied branch) -> dict."""
+    p = chunks_to_steps(rewards, dones, values, loss_mask, loss_mask_sum, reward_type,
+                        need_values=(adv_type == "gae"))
+    if adv_type == "gae":
+        extra = {k: kw[k] for k in ("normalize_advantages", "normalize_returns") if k in kw}
+        adv, ret = gae(p["rewards"], p["values"], p["dones"], gamma, gae_lambda,
+                       p["loss_mask"], **extra)
+    elif adv_type == "grpo":
+        sc = first_episode_scores(p["rewards"], p["dones"])
+        adv, ret = grpo_group_advantages(sc, p["loss_mask"], group_size), None
+    else:
+        raise ValueError(adv_type)
+    out = {"advantages": steps_to_chunks(adv, p["num_chunk"], p["chunk_size"])}
+    if ret is not None:
+        out["returns"] = steps_to_chunks(ret, p["num_chunk"], p["chunk_size"])
+    return out
+
+
+def adv_and_returns_reasoning(adv_type, rewards, loss_mask, values=None, gamma=1.0,
+                              gae_lambda=1.0, group_size=8, **kw):
+    """rlinf/algorithms/registry.py:119-124 + utils.py:177-277 (reasoning branch).
+
+    rewards [bsz]; loss_mask/values [bsz, L] -> (adv [bsz,L], ret [bsz,L] | None).
+    """
+    bsz, seqlen = loss_mask.shape
+    m = loss_mask.transpose(0, 1)
+    if adv_type == "gae":
+        r = torch.zeros((seqlen, bsz), dtype=rewards.dtype)
+        r[-1] = rewards
+        v = None
+        if values is not None:
+            v = torch.cat([values.transpose(0, 1), torch.zeros((1, bsz), dtype=values.dtype)], 0)
+        d = torch.zeros(seqlen + 1, bsz, dtype=torch.bool)
+        d[-1] = True
+        extra = {k: kw[k] for k in ("normalize_advantages", "normalize_returns") if k in kw}
+        adv, ret = gae(r, v, d, gamma, gae_lambda, m, **extra)
+    elif adv_type == "grpo":
+        adv, ret = grpo_group_advantages(rewards.reshape(-1, group_size), m, group_size), None
+    else:
+        raise ValueError(adv_type)
+    adv = adv.transpose(0, 1).contiguous()
+    if ret is not None:
+        ret = ret.transpose(0, 1).contiguous()
+    return adv, ret
+
+
+def reward_filter_mask(rewards, loss_mask, group_size, lower, upper):
+    """rlinf/workers/actor/embodied_fsdp_actor_worker.py:236-282 -> bool [nc,B,1]."""
+    if loss_mask is not None:
+        rewards = rewards * loss_mask
+    nc, bsz, _ = rewards.shape
+    per_env = rewards.transpose(0, 1).reshape(bsz, -1)
+    grp_mean = per_env.reshape(bsz // group_size, group_size, -1).sum(-1).mean(1)
+    keep = ((grp_mean >= lower) & (grp_mean <= upper)).repeat_interleave(group_size)
+    keep = keep.unsqueeze(0).expand(nc, -1).unsqueeze(-1)
+    return (keep & loss_mask) if loss_mask is not None else keep
+
+
+# --------------------------------------------------------------------------
+# trajectory indexing
+# --------------------------------------------------------------------------
+
+_T_PLUS_ONE_KEYS = ("dones", "terminations", "truncations", "prev_values")
+
+
+def merge_rollout_epochs(batch, rollout_epoch):
+    """rlinf/utils/nested_dict_process.py:251-269: [E*nc,B,..] -> [nc,E*B,..]."""
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, dict):
+            out[k] = merge_rollout_epochs(v, rollout_epoch)
+        elif isinstance(v, torch.Tensor):
+            x = v.reshape(rollout_epoch, -1, *v.shape[1:]).transpose(0, 1)
+            out[k] = x.reshape(x.shape[0], -1, *x.shape[3:])
+    return out
+
+
+def shuffle_indices(n, seed):
+    """embodied_fsdp_actor_worker.py:511-513: CPU mt19937 randperm, seed+rank."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
+def flatten_and_shuffle(batch, perm):
+    """rlinf/utils/nested_dict_process.py:272-285: drop the bootstrap row of the
+    (T+1)-row tensors, flatten [T,B,..] -> [T*B,..] (index t*B+b), gather by perm."""
+    out = {}
+    for k, v in batch.items():
+        if v is None:
+            out[k] = None
+        elif isinstance(v, dict):
+            out[k] = flatten_and_shuffle(v, perm)
+        elif isinstance(v, torch.Tensor):
+            if k in _T_PLUS_ONE_KEYS:
+                v = v[:-1]
+            out[k] = v.reshape(-1, *v.shape[2:])[perm]
+    return out
+
+
+# --------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------
+
+
+def _to_rank(t, shape):
+    if t is None:
+        return None
+    while t.dim() < len(shape) and t.shape != shape:
+        t = t.unsqueeze(-1)
+    return t
+
+
+def reduce_loss_inputs(logprobs, old_logprobs, advantages, logprob_type, single_action_dim,
+                       loss_mask=None, loss_mask_sum=None, values=None, prev_values=None,
+                       returns=None, reward_type="action_level"):
+    """rlinf/algorithms/utils.py:280-376 (preprocess_loss_inputs)."""
+    if reward_type == "chunk_level":
+        flat = lambda t: None if t is None else t.flatten()  # noqa: E731
+        advantages, loss_mask, loss_mask_sum = flat(advantages), flat(loss_mask), flat(loss_mask_sum)
+        values, prev_values, returns = flat(values), flat(prev_values), flat(returns)
+    bsz = logprobs.shape[0]
+    if logprob_type == "token_level":
+        logprobs = logprobs.reshape(bsz, -1, single_action_dim)
+        old_logprobs = old_logprobs.reshape(bsz, -1, single_action_dim)
+        advantages = advantages.unsqueeze(-1)
+        loss_mask = None if loss_mask is None else loss_mask.unsqueeze(-1)
+        loss_mask_sum = None if loss_mask_sum is None else loss_mask_sum.unsqueeze(-1)
+    elif logprob_type == "action_level":
+        logprobs = logprobs.reshape(bsz, -1, single_action_dim).sum(-1)
+        old_logprobs = old_logprobs.reshape(bsz, -1, single_action_dim).sum(-1)
+    elif logprob_type == "chunk_level":
+        logprobs = logprobs.reshape(bsz, -1, single_action_dim).sum(dim=[1, 2])
+        old_logprobs = old_logprobs.reshape(bsz, -1, single_action_dim).sum(dim=[1, 2])
+    shp = logprobs.shape
+    return dict(logprobs=logprobs, old_logprobs=old_logprobs,
+                advantages=_to_rank(advantages, shp), loss_mask=_to_rank(loss_mask, shp),
+                loss_mask_sum=_to_rank(loss_mask_sum, shp), values=_to_rank(values, shp),
+                prev_values=_to_rank(prev_values, shp), returns=_to_rank(returns, shp))
+
+
+def ppo_actor_loss(logprobs, old_logprobs, advantages, clip_ratio_low, clip_ratio_high,
+                   loss_mask=None, clip_ratio_c=None, max_episode_steps=None,
+                   loss_mask_sum=None, critic_warmup=False, clip_log_ratio_min=None,
+                   clip_log_ratio_max=None, **_):
+    """rlinf/algorithms/losses.py:170-312 (compute_ppo_actor_loss)."""
+    agg, wratio = masked_mean, None
+    if max_episode_steps is not None and loss_mask_sum is not None and loss_mask is not None:
+        wratio = (loss_mask_sum * 1.0) / max_episode_steps
+        agg = masked_mean_ratio
+    if loss_mask is None:
+        loss_mask = torch.ones_like(logprobs).bool()
+    cnt = float(int(loss_mask.count_nonzero()) or 1)
+    lr = logprobs - old_logprobs
+    if clip_log_ratio_min is not None:
+        lr = torch.clamp(lr, min=clip_log_ratio_min)
+    if clip_log_ratio_max is not None:
+        lr = torch.clamp(lr, max=clip_log_ratio_max)
+    ratio = torch.where(loss_mask, torch.exp(lr), 0)
+    kl_terms = torch.where(loss_mask, lr.detach(), 0.0)
+    clipped = torch.clamp(ratio, 1.0 - clip_ratio_low, 1.0 + clip_ratio_high)
+    l1, l2 = -advantages * ratio, -advantages * clipped
+    clip_hit = l1.detach() < l2.detach()
+    loss_e = torch.max(l1, l2)
+    if clip_ratio_c is not None:
+        assert clip_ratio_c > 1.0
+        l3 = torch.sign(advantages) * clip_ratio_c * advantages
+        dual_hit = l3.detach() < loss_e.detach()
+        loss_e = torch.min(loss_e, l3)
+    else:
+        dual_hit = torch.zeros_like(clip_hit)
+    args = (loss_mask,) if agg is masked_mean else (loss_mask, wratio)
+    loss_abs = agg(loss_e.abs(), *args)
+    loss = agg(loss_e, *args)
+    dual_hit = (dual_hit * loss_mask).bool()
+    clip_fraction = (clip_hit * loss_mask).sum() / cnt
+    approx_kl = -kl_terms.sum() / cnt
+    dual_ratio = torch.where(dual_hit, ratio, 0)
+    if critic_warmup:
+        loss = torch.tensor(0.0)
+    mm = loss_mask
+    if ratio.dim() > 2 and loss_mask.shape[-1] == 1 and ratio.shape[-1] > 1:
+        mm = loss_mask.expand_as(ratio)
+    rd = ratio.detach()
+    metrics = {
+        "actor/policy_loss": loss.detach(),
+        "actor/policy_loss_abs": loss_abs.detach(),
+        "actor/ratio": masked_mean(rd, mm),
+        "actor/ratio_abs": masked_mean((rd - 1).abs(), mm),
+        "actor/clipped_ratio": masked_mean(clipped.detach(), mm),
+        "actor/dual_cliped_ratio": masked_mean(dual_ratio.detach(), mm),
+        "actor/approx_kl": approx_kl.detach(),
+        "actor/clip_fraction": clip_fraction.detach(),
+    }
+    return loss, metrics
+
+
+EV_PREFIX = "__sum__/_critic_explained_variance/"
+
+
+def ppo_critic_loss(values, returns, prev_values, value_clip, huber_delta, loss_mask=None,
+                    max_episode_steps=None, loss_mask_sum=None, **_):
+    """rlinf/algorithms/losses.py:315-380 + metric_utils.py:232-258."""
+    agg, wratio = masked_mean, None
+    if max_episode_steps is not None and loss_mask_sum is not None and loss_mask is not None:
+        wratio = (loss_mask_sum * 1.0) / max_episode_steps
+        agg = masked_mean_ratio
+    v_clipped = prev_values + (values - prev_values).clamp(-value_clip, value_clip)
+    l_orig = huber(returns - values, huber_delta)
+    l_clip = huber(returns - v_clipped, huber_delta)
+    le = torch.max(l_orig, l_clip)
+    loss = agg(le, loss_mask) if agg is masked_mean else agg(le, loss_mask, wratio)
+    clip_ratio = ((v_clipped - prev_values).abs() > value_clip).float().mean()
+    r, v = returns.detach().float(), values.detach().float()
+    if loss_mask is not None:
+        mk = torch.broadcast_to(loss_mask.bool(), r.shape)
+        r, v = r[mk], v[mk]
+    else:
+        r, v = r.reshape(-1), v.reshape(-1)
+    e = r - v
+    metrics = {
+        "critic/value_loss": loss.detach(),
+        "critic/value_clip_ratio": clip_ratio.detach(),
+        EV_PREFIX + "count": torch.tensor(float(r.numel())),
+        EV_PREFIX + "returns_sum": r.sum(),
+        EV_PREFIX + "returns_sq_sum": (r * r).sum(),
+        EV_PREFIX + "errors_sum": e.sum(),
+        EV_PREFIX + "errors_sq_sum": (e * e).sum(),
+    }
+    return loss, metrics
+
+
+def policy_loss_embodied(loss_type, logprobs, old_logprobs, advantages, logprob_type,
+                         single_action_dim, loss_mask=None, loss_mask_sum=None, values=None,
+                         prev_values=None, returns=None, reward_type="action_level", **hp):
+    """rlinf/algorithms/registry.py:77-92 (embodied) + losses.py:396-424,508-535."""
+    p = reduce_loss_inputs(logprobs, old_logprobs, advantages, logprob_type, single_action_dim,
+                           loss_mask, loss_mask_sum, values, prev_values, returns, reward_type)
+    loss, metrics = ppo_actor_loss(p["logprobs"], p["old_logprobs"], p["advantages"],
+                                   loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"], **hp)
+    if loss_type == "actor_critic":
+        closs, cmetrics = ppo_critic_loss(p["values"], p["returns"], p["prev_values"],
+                                          hp["value_clip"], hp["huber_delta"],
+                                          loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"],
+                                          max_episode_steps=hp.get("max_episode_steps"))
+        loss = loss + closs
+        metrics.update(cmetrics)
+    elif loss_type != "actor":
+        raise ValueError(loss_type)
+    return loss, {k: (float(v) if isinstance(v, torch.Tensor) else v) for k, v in metrics.items()}
+
+
+def entropy_term(entropy, entropy_type, action_dim, batch_size, loss_mask):
+    """rlinf/utils/utils.py:384-408 + embodied_fsdp_actor_worker.py:680-689."""
+    if entropy_type == "action_level":
+        entropy = entropy.reshape(batch_size, -1, action_dim).sum(-1)
+    elif entropy_type == "chunk_level":
+        entropy = entropy.sum(-1)
+    return masked_mean(entropy, loss_mask)
+
+
+# --------------------------------------------------------------------------
+# MLP policy (models/embodiment/mlp_policy/mlp_policy.py, modules/value_head.py)
+# --------------------------------------------------------------------------
+
+HIDDEN = 256
+_HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+
+
+def mlp_param_shapes(obs_dim, act_dim, num_action_chunks=1, value_out=None):
+    """Parameter names/shapes in `named_parameters()` order of the reference
+    MLPPolicy (mlp_policy.py:28-105): own Parameter first, then children in
+    construction order (value_head, backbone, actor_mean)."""
+    ca = num_action_chunks * act_dim
+    vo = num_action_chunks if value_out is None else value_out
+    return [
+        ("actor_logstd", (1, ca)),
+        ("value_head.mlp.0.weight", (HIDDEN, obs_dim)), ("value_head.mlp.0.bias", (HIDDEN,)),
+        ("value_head.mlp.2.weight", (HIDDEN, HIDDEN)), ("value_head.mlp.2.bias", (HIDDEN,)),
+        ("value_head.mlp.4.weight", (HIDDEN, HIDDEN)), ("value_head.mlp.4.bias", (HIDDEN,)),
+        ("value_head.mlp.6.weight", (vo, HIDDEN)),
+        ("backbone.0.weight", (HIDDEN, obs_dim)), ("backbone.0.bias", (HIDDEN,)),
+        ("backbone.2.weight", (HIDDEN, HIDDEN)), ("backbone.2.bias", (HIDDEN,)),
+        ("backbone.4.weight", (HIDDEN, HIDDEN)), ("backbone.4.bias", (HIDDEN,)),
+        ("actor_mean.weight", (ca, HIDDEN)), ("actor_mean.bias", (ca,)),
+    ]
+
+
+def mlp_init(obs_dim, act_dim, num_action_chunks=1, seed=0):
+    """Random init with the reference's distributions (mlp_policy.py:91-105 ->
+    modules/utils.py layer_init: orthogonal(sqrt 2) weights, zero bias;
+    value_head.py:50-63: kaiming_normal fan_out / N(0,0.02) last layer)."""
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    for name, shape in mlp_param_shapes(obs_dim, act_dim, num_action_chunks):
+        if name == "actor_logstd":
+            p[name] = torch.full(shape, -0.5)
+        elif name.endswith("bias"):
+            p[name] = torch.zeros(shape)
+        elif name.startswith("value_head"):
+            if name == "value_head.mlp.6.weight":
+                p[name] = torch.randn(shape, generator=g) * 0.02
+            else:  # kaiming_normal_(mode="fan_out", nonlinearity="tanh"): gain 5/3
+                p[name] = torch.randn(shape, generator=g) * ((5.0 / 3.0) / math.sqrt(shape[0]))
+        else:
+            w = torch.empty(shape)
+            torch.nn.init.orthogonal_(w, gain=(0.01 * math.sqrt(2)) if name.startswith("actor_mean") else math.sqrt(2), generator=g)
+            p[name] = w
+    return p
+
+
+def mlp_forward(params, states, action=None, want_entropy=True, want_values=True):
+    """mlp_policy.py:202-236 (default_forward): tanh MLP 3x256 -> mean;
+    state-independent logstd; Normal log_prob / entropy; value MLP 3x256 -> C."""
+    F = torch.nn.functional
+    h = states
+    for i in (0, 2, 4):
+        h = torch.tanh(F.linear(h, params[f"backbone.{i}.weight"], params[f"backbone.{i}.bias"]))
+    mean = F.linear(h, params["actor_mean.weight"], params["actor_mean.bias"])
+    logstd = params["actor_logstd"].expand_as(mean)
+    std = torch.exp(logstd)
+    out = {"mean": mean, "logstd": logstd}
+    if action is not None:
+        var = std**2
+        out["logprobs"] = -((action - mean) ** 2) / (2 * var) - std.log() - _HALF_LOG_2PI
+    if want_entropy:
+        out["entropy"] = 0.5 + _HALF_LOG_2PI + torch.log(std)
+    if want_values:
+        v = states
+        for i in (0, 2, 4):
+            v = torch.tanh(F.linear(v, params[f"value_head.mlp.{i}.weight"], params[f"value_head.mlp.{i}.bias"]))
+        out["values"] = F.linear(v, params["value_head.mlp.6.weight"])
+    return out
+
+
+def mlp_sample(params, states, noise):
+    """mlp_policy.py:256-293 (_generate_actions, mode="train") with the N(0,1)
+    draw supplied by the caller (parity is on GIVEN noise, not on the RNG):
+    action = mean + std * noise; log_prob; value."""
+    out = mlp_forward(params, states, None, want_entropy=False, want_values=True)
+    std = torch.exp(out["logstd"])
+    action = out["mean"] + std * noise
+    var = std**2
+    logp = -((action - out["mean"]) ** 2) / (2 * var) - std.log() - _HALF_LOG_2PI
+    return action, logp, out["values"]
+
+
+# --------------------------------------------------------------------------
+# optimiser (hybrid_engines/fsdp/fsdp_model_manager.py:429-463,501-590; no_shard
+# path of strategy/fsdp.py:363-369 = torch.nn.utils.clip_grad_norm_)
+# --------------------------------------------------------------------------
+
+
+def build_adamw(params: dict, lr, value_lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    actor = [p for n, p in params.items() if "value_head" not in n]
+    critic = [p for n, p in params.items() if "value_head" in n]
+    groups = [{"params": actor, "lr": lr, "betas": betas}]
+    if critic:
+        groups.append({"params": critic, "lr": value_lr, "betas": betas})
+    return torch.optim.AdamW(groups, eps=eps, weight_decay=weight_decay)
+
+
+def optimizer_step(optimizer, params: dict, clip_grad):
+    gn = torch.nn.utils.clip_grad_norm_(list(params.values()), clip_grad)
+    if torch.isfinite(gn):
+        optimizer.step()
+    return float(gn)
+
+
+def adamw_reference_math(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=1e-2):
+    """Closed form of one torch.optim.AdamW step (single-tensor path) for
+    known-answer checks of the flat-buffer kernel."""
+    p = p * (1 - lr * wd)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1**step, 1 - beta2**step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    p = p - (lr / bc1) * m / denom
+    return p, m, v
