@@ -1,0 +1,248 @@
+/*
+ * rlinf_b200.h - C ABI of librlinf_b200.so: the B200-native (sm_100a) drop-in for the
+ * data-parallel hot path of RLinf's actor-learner (advantages, PPO/GRPO loss,
+ * MLP policy forward/backward, grad-clip + AdamW, rollout sampling).
+ *
+ * Conventions:
+ *  - plain pointers and sizes; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - every entry point takes a `stream` (a cudaStream_t passed as void*), never synchronises
+ *    the device, allocates nothing the caller can see, and owns no state except a lazily
+ *    created per-device scratch (a few KB of reduction slots, TMA descriptors);
+ *  - outputs are caller-allocated; inputs are never mutated;
+ *  - return value: 0 = ok, <0 = invalid argument (RB200_E_*), >0 = a cudaError_t;
+ *  - bool tensors are 1 byte per element (torch.bool / uint8), fp tensors are float32
+ *    (the reference asserts fp32: rlinf/algorithms/losses.py:232-240).
+ *
+ * Each entry point cites the reference interface it replaces (file:line under the
+ * RLinf v0.4.0 tree).  The reference is 100 % Python; the binding a maintainer
+ * would add is a ctypes stub, shown in INTEGRATION.md.
+ */
+#ifndef RLINF_B200_H
+#define RLINF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB200_ABI_VERSION 1
+
+/* error codes (<0); >0 is a cudaError_t */
+#define RB200_OK 0
+#define RB200_E_NULL (-1)      /* required pointer is NULL */
+#define RB200_E_SHAPE (-2)     /* non-positive / inconsistent dimension */
+#define RB200_E_ARG (-3)       /* bad scalar argument (e.g. clip_ratio_c <= 1) */
+#define RB200_E_ALIGN (-4)     /* pointer not aligned as required */
+#define RB200_E_UNSUPPORTED (-5)
+
+typedef void* rb200_stream_t; /* cudaStream_t */
+
+int rb200_abi_version(void);
+const char* rb200_strerror(int code);
+/* sm count / compute capability of the current device (host-side query). */
+int rb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  loss mask            replaces compute_loss_mask, rlinf/utils/metric_utils.py:516-537
+ *   dones     bool  [(nc+1), B, C]
+ *   mask      bool  [nc, B, C]        step valid while no done seen in rows [0..t]
+ *   mask_sum  int64 [B]               per-env valid-step count (the reference expands it
+ *                                     to mask's shape as a view; the shim does the same)
+ * ---------------------------------------------------------------------------------------- */
+int rb200_loss_mask(const uint8_t* dones, uint8_t* mask, int64_t* mask_sum,
+                    int nc, int B, int C, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  GAE scan (+ normalisation statistics)
+ *   replaces compute_gae_advantages_and_returns, rlinf/algorithms/advantages.py:24-86
+ *   (the T-iteration Python loop) and the statistics half of safe_normalize,
+ *   rlinf/algorithms/utils.py:397-404.
+ *   Step-major layout: rewards [T,B] f32, values [T+1,B] f32 (NULL = critic-free: gamma=lambda=1,
+ *   delta=r), dones [T+1,B] bool, loss_mask [T,B] bool or NULL.
+ *   adv, ret [T,B] f32 are the UN-normalised outputs, bit-identical to the reference's fp32
+ *   sequential recurrence (each op rounded separately, no FMA contraction).
+ *   stats (may be NULL): double[6] = {n, sum, sumsq} of adv over valid entries, then of ret.
+ *   The caller zeroes nothing: the call resets stats itself.
+ *   gamma / gae_lambda are doubles because the reference rounds fl32(gamma) for gamma*V but
+ *   fl32(gamma*gae_lambda) (product taken in Python double) for the recurrence coefficient.
+ * ---------------------------------------------------------------------------------------- */
+int rb200_gae(const float* rewards, const float* values, const uint8_t* dones,
+              const uint8_t* loss_mask, float* adv, float* ret, double* stats,
+              int T, int B, double gamma, double gae_lambda, rb200_stream_t stream);
+
+/* x <- (x - mean) / (std_unbiased + eps) with {n,sum,sumsq} = stats[0..2]; no-op if n == 0.
+ * The apply half of safe_normalize (eps=1e-5, rlinf/algorithms/utils.py:397-404). In place. */
+int rb200_normalize(float* x, const double* stats, int64_t n_elems, float eps,
+                    rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1' GRPO: first-episode scores + group normalisation + broadcast over T
+ *   replaces calculate_scores, rlinf/algorithms/utils.py:134-152 (CPU-only reverse loop) and
+ *   compute_grpo_advantages, rlinf/algorithms/advantages.py:89-121.
+ *   rewards [T,B] f32, dones [T+1,B] bool -> scores [B] f32 (bit-identical reverse accumulation)
+ *   scores [B] (groups of G consecutive envs), loss_mask [T,B] bool -> adv [T,B] f32
+ * ---------------------------------------------------------------------------------------- */
+int rb200_grpo_scores(const float* rewards, const uint8_t* dones, float* scores,
+                      int T, int B, rb200_stream_t stream);
+int rb200_grpo_advantages(const float* scores, const uint8_t* loss_mask, float* adv,
+                          int T, int B, int G, float eps, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a12 trajectory gather    replaces process_nested_dict_for_train's
+ *   `value.reshape(-1, ...)[shuffle_id]`, rlinf/utils/nested_dict_process.py:272-285.
+ *   dst[i, :] = src[idx[i], :] for rows of `row_bytes` bytes (any dtype). idx is int64.
+ * ---------------------------------------------------------------------------------------- */
+int rb200_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_rows_out,
+                      int64_t n_rows_src, int64_t row_bytes, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  fused (gather +) PPO actor[-critic] loss, forward + backward in one pass
+ *   replaces policy_loss, rlinf/algorithms/registry.py:77-92, preprocess_loss_inputs
+ *   (algorithms/utils.py:280-376), compute_ppo_actor_loss (losses.py:170-312),
+ *   compute_ppo_critic_loss (losses.py:315-380), the entropy term and 1/grad_accum scaling of
+ *   embodied_fsdp_actor_worker.py:678-695, and autograd's backward of all of it.
+ * ---------------------------------------------------------------------------------------- */
+enum { RB200_LOGPROB_TOKEN = 0, RB200_LOGPROB_ACTION = 1, RB200_LOGPROB_CHUNK = 2 };
+
+/* indices into the metrics vector written by rb200_ppo_loss */
+enum {
+  RB200_M_POLICY_LOSS = 0,      /* actor/policy_loss        */
+  RB200_M_POLICY_LOSS_ABS = 1,  /* actor/policy_loss_abs    */
+  RB200_M_RATIO = 2,            /* actor/ratio              */
+  RB200_M_RATIO_ABS = 3,        /* actor/ratio_abs          */
+  RB200_M_CLIPPED_RATIO = 4,    /* actor/clipped_ratio      */
+  RB200_M_DUAL_CLIPPED_RATIO = 5, /* actor/dual_cliped_ratio (sic, reference spelling) */
+  RB200_M_APPROX_KL = 6,        /* actor/approx_kl          */
+  RB200_M_CLIP_FRACTION = 7,    /* actor/clip_fraction      */
+  RB200_M_VALUE_LOSS = 8,       /* critic/value_loss        */
+  RB200_M_VALUE_CLIP_RATIO = 9, /* critic/value_clip_ratio  */
+  RB200_M_EV_COUNT = 10,        /* __sum__/_critic_explained_variance/count          */
+  RB200_M_EV_RET_SUM = 11,      /*   .../returns_sum     */
+  RB200_M_EV_RET_SQ_SUM = 12,   /*   .../returns_sq_sum  */
+  RB200_M_EV_ERR_SUM = 13,      /*   .../errors_sum      */
+  RB200_M_EV_ERR_SQ_SUM = 14,   /*   .../errors_sq_sum   */
+  RB200_M_ENTROPY = 15,         /* actor/entropy_loss (masked mean entropy, before the bonus) */
+  RB200_M_TOTAL_LOSS = 16,      /* actor/total_loss  (after entropy bonus and loss_scale)     */
+  RB200_M_TOKEN_NUM = 17,       /* number of valid loss entries (count_nonzero of the mask)    */
+  RB200_NUM_METRICS = 24
+};
+
+typedef struct rb200_ppo_args {
+  /* shapes: bsz samples x C chunks x A action dims. A "unit" is one (sample, chunk) for
+   * token/action level and one sample for chunk level; U = units per sample (C or 1). */
+  int64_t bsz;
+  int32_t C, A;
+  int32_t logprob_type; /* RB200_LOGPROB_* */
+  int32_t with_critic;  /* 1: actor_critic, 0: actor only */
+  /* current policy outputs for this micro-batch (NOT gathered) */
+  const float* logprobs; /* [bsz, C*A] */
+  const float* values;   /* [bsz, U] or NULL */
+  const float* entropy;  /* [bsz, C*A] or NULL (entropy bonus term, action-level reduction) */
+  /* rollout data; row i of the micro-batch lives at row (idx ? idx[i] : i) */
+  const int64_t* idx;          /* [bsz] or NULL */
+  const float* old_logprobs;   /* [rows, C*A] */
+  const float* advantages;     /* [rows, U] */
+  const float* returns;        /* [rows, U] or NULL */
+  const float* prev_values;    /* [rows, U] or NULL */
+  const uint8_t* loss_mask;    /* [rows, U] or NULL */
+  const int64_t* loss_mask_sum; /* [rows or mask_sum_rows, U] or NULL */
+  int64_t mask_sum_row_mod;    /* >0: loss_mask_sum row = row % mask_sum_row_mod (per-env table) */
+  /* deferred advantage normalisation: if non-NULL, advantages are normalised on the fly with
+   * {n,sum,sumsq} = adv_stats[0..2] and eps adv_norm_eps (fusion of safe_normalize) */
+  const double* adv_stats;
+  float adv_norm_eps;
+  /* hyper-parameters (losses.py:170-186, 315-325). Doubles: the reference holds them as Python
+   * floats and rounds derived bounds (e.g. 1.0 - clip_ratio_low) once, from double. */
+  double clip_ratio_low, clip_ratio_high;
+  double clip_ratio_c;      /* <= 0: no dual clip; else must be > 1 */
+  int32_t has_clip_log_ratio_min, has_clip_log_ratio_max;
+  double clip_log_ratio_min, clip_log_ratio_max;
+  double value_clip, huber_delta;
+  int32_t max_episode_steps; /* >0 with mask+mask_sum: masked_mean_ratio aggregation */
+  int32_t critic_warmup;     /* 1: policy loss := 0 (no actor grads) */
+  double entropy_bonus;      /* 0: none */
+  double loss_scale;         /* 1/gradient_accumulation */
+  /* scratch: caller-provided, >= 32 doubles, contents ignored and overwritten */
+  double* workspace;
+  /* outputs */
+  float* loss;        /* [1] total loss (after entropy bonus and loss_scale) */
+  float* metrics;     /* [RB200_NUM_METRICS] */
+  float* d_logprobs;  /* [bsz, C*A] or NULL */
+  float* d_values;    /* [bsz, U] or NULL */
+  float* d_entropy;   /* [bsz, C*A] or NULL */
+} rb200_ppo_args;
+
+int rb200_ppo_loss(const rb200_ppo_args* args, rb200_stream_t stream);
+
+/* x[i] *= s (device scalar-free helper for autograd's upstream scalar). */
+int rb200_scale(float* x, int64_t n, float s, rb200_stream_t stream);
+/* x[i] *= *s_dev  (the scalar lives on the device: no host sync in autograd's backward). */
+int rb200_scale_by(float* x, int64_t n, const float* s_dev, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  grad-norm clip + AdamW on one flat fp32 buffer
+ *   replaces FSDPModelManager.optimizer_step, hybrid_engines/fsdp/fsdp_model_manager.py:429-463
+ *   (clip_grad_norm_ of the no_shard path strategy/fsdp.py:363-369 = torch.nn.utils.clip_grad_norm_:
+ *   coef = min(1, max_norm/(norm+1e-6)); non-finite norm => step skipped) and torch.optim.AdamW
+ *   with the two lr groups of build_optimizer :501-590.
+ *   group_end[k] = exclusive end offset of lr group k in the flat buffer (ascending).
+ *   state: double[4] device = {step_count, last_grad_norm, last_clip_coef, skipped_flag}.
+ * ---------------------------------------------------------------------------------------- */
+int rb200_grad_sqnorm(const float* grads, int64_t n, double* out_sq /*[1], reset by kernel*/,
+                      rb200_stream_t stream);
+int rb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, const int64_t* group_end_host, const double* group_lr_host,
+                     int n_groups, double beta1, double beta2, double eps, double weight_decay,
+                     float max_grad_norm, float grad_scale, const double* grad_sq /*[1]*/,
+                     double* state /*[4]*/, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3/K5  MLP policy (3x256 tanh backbone + mean head, state-independent log-std, 3x256 value
+ *   MLP).  replaces MLPPolicy.default_forward, models/embodiment/mlp_policy/mlp_policy.py:202-236,
+ *   ValueHead.forward, models/embodiment/modules/value_head.py:66, _generate_actions :256-293,
+ *   and autograd's backward through them.  Declared in the second half of this header
+ *   (rb200_mlp_*), see below.
+ * ---------------------------------------------------------------------------------------- */
+
+/* flat parameter layout, in the reference's named_parameters() order */
+typedef struct rb200_mlp_layout {
+  int32_t obs_dim, act_dim /* C*A outputs of the mean head */, value_dim, hidden /* 256 */;
+  int64_t logstd;                         /* [act_dim] */
+  int64_t vw0, vb0, vw1, vb1, vw2, vb2, vw3; /* value head: [H,obs],[H],[H,H],[H],[H,H],[H],[value_dim,H] */
+  int64_t bw0, bb0, bw1, bb1, bw2, bb2;   /* backbone */
+  int64_t mw, mb;                         /* actor_mean [act_dim,H],[act_dim] */
+  int64_t total;                          /* number of floats */
+} rb200_mlp_layout;
+
+int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_dim, int value_dim, int hidden);
+
+/* scratch sizes (floats) for n rows */
+int64_t rb200_mlp_fwd_scratch_floats(const rb200_mlp_layout* L, int64_t n);
+
+/* Forward for training: states [n,obs] (row i at idx?idx[i]:i), action [n,act] (same gather).
+ * Writes logprobs [n,act], entropy [n,act] (NULL ok), values [n,value_dim] (NULL ok) and keeps
+ * the activations needed by backward in `acts` (rb200_mlp_fwd_scratch_floats floats). */
+int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* states,
+                      const float* action, const int64_t* idx, int64_t n, float* logprobs,
+                      float* entropy, float* values, float* acts, rb200_stream_t stream);
+
+/* Backward: given d_logprobs [n,act], d_entropy [n,act] or NULL, d_values [n,value_dim] or NULL,
+ * ACCUMULATES (+=) parameter gradients into grads (flat, same layout). `acts` from forward;
+ * `work` is scratch of the same size as acts. */
+int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* states,
+                       const float* action, const int64_t* idx, int64_t n,
+                       const float* d_logprobs, const float* d_entropy, const float* d_values,
+                       const float* acts, float* work, float* grads, rb200_stream_t stream);
+
+/* Rollout step (inference): mean/value forward, action = mean + exp(logstd)*noise where noise is
+ * either supplied ([n,act], parity mode) or drawn from Philox(seed, offset) (noise == NULL);
+ * writes action [n,act], logprobs [n,act], values [n,value_dim]. */
+int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* states,
+                     const float* noise, uint64_t seed, uint64_t offset, int64_t n, float* action,
+                     float* logprobs, float* values, float* work, rb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLINF_B200_H */

@@ -1,0 +1,15 @@
+"""`rlinf_b200.algorithms` - the reference's `rlinf.algorithms` plugin surface, CUDA-backed.
+
+Importing the package fills the registries, like rlinf/algorithms/__init__.py:16.
+"""
+from . import advantages, losses  # noqa: F401  (registration side effects)
+from .registry import (  # noqa: F401
+    ADV_REGISTRY,
+    LOSS_REGISTRY,
+    calculate_adv_and_returns,
+    get_adv_and_returns,
+    get_policy_loss,
+    policy_loss,
+    register_advantage,
+    register_policy_loss,
+)

@@ -1,0 +1,92 @@
+"""Plugin registries and the two operator entry points, with the reference's surface.
+
+Mirror of rlinf/algorithms/registry.py: `ADV_REGISTRY` (:30), `register_advantage` (:33),
+`get_adv_and_returns` (:47), `LOSS_REGISTRY` (:56), `register_policy_loss` (:59),
+`get_policy_loss` (:71), `policy_loss` (:77-92), `calculate_adv_and_returns` (:95-124).
+Same names, kwargs, return conventions (embodied -> dict, reasoning -> tuple) and error behaviour;
+the registered callables launch the sm_100a kernels of librlinf_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .utils import (
+    calculate_scores,
+    postprocess_embodied_advantages_outputs,
+    postprocess_reasoning_advantages_outputs,
+    preprocess_embodied_advantages_inputs,
+    preprocess_reasoning_advantages_inputs,
+)
+
+ADV_REGISTRY: dict[str, Callable] = {}
+LOSS_REGISTRY: dict[str, Callable] = {}
+
+
+def register_advantage(name: str):
+    def decorator(fn):
+        ADV_REGISTRY[name.lower()] = fn
+        return fn
+
+    return decorator
+
+
+def get_adv_and_returns(name: str) -> Callable:
+    if name.lower() not in ADV_REGISTRY:
+        raise ValueError(f"Advantage '{name}' not registered. Available: {list(ADV_REGISTRY.keys())}")
+    return ADV_REGISTRY[name.lower()]
+
+
+def register_policy_loss(name: str):
+    def decorator(fn):
+        LOSS_REGISTRY[name.lower()] = fn
+        return fn
+
+    return decorator
+
+
+def get_policy_loss(name: str):
+    if name not in LOSS_REGISTRY:
+        raise ValueError(f"Loss {name} not registered")
+    return LOSS_REGISTRY[name]
+
+
+def policy_loss(**kwargs) -> tuple[torch.Tensor, dict]:
+    """Unified loss entry (registry.py:77-92).
+
+    For the embodied task type the whole chain preprocess_loss_inputs -> loss fn -> autograd backward
+    is one fused kernel group (the logprob reduction happens inside the kernel), and the metric dict
+    holds Python floats obtained with ONE device->host copy (the reference does one .item() per metric).
+    """
+    from . import losses
+
+    loss_type = kwargs["loss_type"]
+    get_policy_loss(loss_type)  # same "not registered" error
+    task_type = kwargs["task_type"]
+    if task_type == "embodied" and loss_type in ("actor_critic", "actor") and LOSS_REGISTRY[loss_type] in (
+            losses.compute_ppo_actor_critic_loss, losses.compute_grpo_actor_loss_fn):
+        return losses.fused_embodied_policy_loss(**kwargs)
+    loss_fn = LOSS_REGISTRY[loss_type]
+    loss, metrics_data = loss_fn(**kwargs)
+    if task_type == "embodied":
+        metrics_data = losses.postprocess_loss_metric(metrics_data)
+    return loss, metrics_data
+
+
+def calculate_adv_and_returns(**kwargs):
+    """Unified advantage entry (registry.py:95-124)."""
+    adv_type = kwargs["adv_type"]
+    fn = get_adv_and_returns(adv_type)
+    task_type = kwargs["task_type"]
+    if task_type == "embodied":
+        kwargs = preprocess_embodied_advantages_inputs(**kwargs)
+        if adv_type not in ("gae", "grpo_video"):
+            kwargs = calculate_scores(**kwargs)
+        advantages, returns = fn(**kwargs)
+        res = postprocess_embodied_advantages_outputs(advantages=advantages, returns=returns, **kwargs)
+    else:
+        kwargs = preprocess_reasoning_advantages_inputs(**kwargs)
+        advantages, returns = fn(**kwargs)
+        res = postprocess_reasoning_advantages_outputs(advantages, returns)
+    return res

@@ -1,0 +1,317 @@
+// K1: GAE reverse scan over [T,B] trajectories + normalisation statistics; normalise kernel.
+// Reference: compute_gae_advantages_and_returns, rlinf/algorithms/advantages.py:24-86 (a Python
+// loop of T iterations x ~8 eager CPU ops) and safe_normalize, rlinf/algorithms/utils.py:397-404.
+//
+// Parity contract: adv/ret are BIT-IDENTICAL to the reference's fp32 arithmetic.  The recurrence
+//     nd = !done[t+1];  delta = (r[t] + (gamma*V[t+1])*nd) - V[t]
+//     g  = delta + ((gamma*lambda)*nd) * g;   ret[t] = g + V[t];   adv[t] = ret[t] - V[t]
+// rounds after every op (no FMA contraction: __fmul_rn/__fadd_rn) and is evaluated in the
+// reference's sequential order.  fp32 addition is not associative, so a re-associated parallel scan
+// over T cannot be bit-exact; instead each trajectory's chain runs sequentially (2 dependent fp32 ops
+// per step ~ 9 cycles -> ~2.5 us for T=512, below the HBM time of the tile) and the memory-level
+// parallelism comes from TMA: one elected thread streams [R x 32] tiles of rewards / values / dones
+// (/ mask) through an S-stage mbarrier ring in shared memory, newest timestep first.
+//
+// HBM traffic (algorithmic): r 4 + V 4 + done 1 (+ mask 1) read, adv 4 + ret 4 written = 17 B/step.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace {
+
+constexpr int kR = 16;  // timesteps per stage
+constexpr int kS = 8;   // pipeline stages
+constexpr int kW = 32;  // trajectories (columns) per CTA = one warp
+
+struct __align__(128) Stage {
+  float r[kR][kW];
+  float v[kR][kW];
+  uint8_t d[kR][kW];
+  uint8_t m[kR][kW];
+};
+static_assert(sizeof(Stage) == 5120, "stage layout");
+
+struct Acc {
+  double n = 0, s = 0, ss = 0;
+  __device__ __forceinline__ void add(float x) {
+    const double xd = (double)x;
+    n += 1.0;
+    s += xd;
+    ss += xd * xd;
+  }
+};
+
+// One step of the recurrence for one trajectory. Kept in one place so both kernels round identically.
+template <bool HAS_V>
+__device__ __forceinline__ void gae_step(float r, float vt, float v_next, uint8_t done_next, float gamma,
+                                         float coef, float& g, float& ret, float& adv) {
+  const float nd = done_next ? 0.0f : 1.0f;
+  float delta;
+  if (HAS_V) {
+    const float boot = __fmul_rn(__fmul_rn(gamma, v_next), nd);
+    delta = __fsub_rn(__fadd_rn(r, boot), vt);
+  } else {
+    delta = r;
+  }
+  g = __fadd_rn(delta, __fmul_rn(__fmul_rn(coef, nd), g));
+  if (HAS_V) {
+    ret = __fadd_rn(g, vt);
+    adv = __fsub_rn(ret, vt);
+  } else {
+    ret = g;
+    adv = g;
+  }
+}
+
+__device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* stats) {
+  double v[6] = {a.n, a.s, a.ss, r.n, r.s, r.ss};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = rb::warp_sum(v[k]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (v[k] != 0.0) atomicAdd(&stats[k], v[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-pipelined kernel. CTA = 2 warps: warp 0 consumes (32 trajectories), warp 1 lane 0 produces.
+// Requires B % 16 == 0 (16-byte global strides for the byte tensors) and 16-byte aligned bases.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_V, bool HAS_MASK, bool HAS_STATS>
+__global__ void __launch_bounds__(64) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r,
+                                                     const __grid_constant__ CUtensorMap tm_v,
+                                                     const __grid_constant__ CUtensorMap tm_d,
+                                                     const __grid_constant__ CUtensorMap tm_m,
+                                                     const float* __restrict__ values, float* __restrict__ adv,
+                                                     float* __restrict__ ret, double* __restrict__ stats, int T,
+                                                     int B, float gamma, float coef) {
+  __shared__ Stage stages[kS];
+  __shared__ __align__(8) uint64_t full_bar[kS];
+  __shared__ __align__(8) uint64_t empty_bar[kS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * kW;
+  const int n_iter = (T + kR - 1) / kR;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kS; ++s) {
+      rb::tma::mbar_init(&full_bar[s], 1);
+      rb::tma::mbar_init(&empty_bar[s], 1);
+    }
+    rb::tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 1) {
+    if (lane == 0) {
+      rb::tma::prefetch_desc(&tm_r);
+      rb::tma::prefetch_desc(&tm_d);
+      if (HAS_V) rb::tma::prefetch_desc(&tm_v);
+      if (HAS_MASK) rb::tma::prefetch_desc(&tm_m);
+      constexpr uint32_t kBytes = sizeof(float) * kR * kW + (HAS_V ? sizeof(float) * kR * kW : 0) + kR * kW +
+                                  (HAS_MASK ? kR * kW : 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kS;
+        const uint32_t ph = (uint32_t)(it / kS) & 1u;
+        rb::tma::mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int t0 = T - (it + 1) * kR;  // may be negative on the last tile: OOB rows are zero-filled
+        rb::tma::mbar_arrive_expect_tx(&full_bar[s], kBytes);
+        rb::tma::load_2d(&stages[s].r[0][0], &tm_r, col0, t0, &full_bar[s]);
+        if (HAS_V) rb::tma::load_2d(&stages[s].v[0][0], &tm_v, col0, t0, &full_bar[s]);
+        rb::tma::load_2d(&stages[s].d[0][0], &tm_d, col0, t0 + 1, &full_bar[s]);  // done AFTER step t
+        if (HAS_MASK) rb::tma::load_2d(&stages[s].m[0][0], &tm_m, col0, t0, &full_bar[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warp ----
+  const int col = col0 + lane;
+  const bool in_range = col < B;
+  float v_next = (HAS_V && in_range) ? values[(size_t)T * B + col] : 0.0f;  // bootstrap row V[T]
+  float g = 0.0f;
+  Acc acc_a, acc_r;
+  for (int it = 0; it < n_iter; ++it) {
+    const int s = it % kS;
+    const uint32_t ph = (uint32_t)(it / kS) & 1u;
+    const int t0 = T - (it + 1) * kR;
+    rb::tma::mbar_wait(&full_bar[s], ph);
+    const Stage& st = stages[s];
+#pragma unroll
+    for (int rr = kR - 1; rr >= 0; --rr) {
+      const int t = t0 + rr;
+      if (t >= 0) {  // warp-uniform
+        const float r = st.r[rr][lane];
+        const float vt = HAS_V ? st.v[rr][lane] : 0.0f;
+        const uint8_t dn = st.d[rr][lane];
+        float rt, ad;
+        gae_step<HAS_V>(r, vt, v_next, dn, gamma, coef, g, rt, ad);
+        v_next = vt;
+        if (in_range) {
+          const size_t o = (size_t)t * B + col;
+          adv[o] = ad;
+          ret[o] = rt;
+          if (HAS_STATS) {
+            const bool valid = HAS_MASK ? (st.m[rr][lane] != 0) : true;
+            if (valid) {
+              acc_a.add(ad);
+              acc_r.add(rt);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) rb::tma::mbar_arrive(&empty_bar[s]);
+  }
+  if (HAS_STATS) flush_stats(acc_a, acc_r, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel (any B, any alignment): one thread per trajectory, register prefetch of U rows.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_V, bool HAS_MASK, bool HAS_STATS>
+__global__ void __launch_bounds__(32) gae_generic_kernel(const float* __restrict__ rewards,
+                                                         const float* __restrict__ values,
+                                                         const uint8_t* __restrict__ dones,
+                                                         const uint8_t* __restrict__ mask, float* __restrict__ adv,
+                                                         float* __restrict__ ret, double* __restrict__ stats, int T,
+                                                         int B, float gamma, float coef) {
+  constexpr int U = 8;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const bool in_range = col < B;
+  Acc acc_a, acc_r;
+  if (in_range) {
+    float v_next = HAS_V ? values[(size_t)T * B + col] : 0.0f;
+    float g = 0.0f;
+    for (int t_hi = T - 1; t_hi >= 0; t_hi -= U) {
+      float r[U], v[U];
+      uint8_t d[U], m[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t_hi - u;
+        const bool ok = t >= 0;
+        const size_t o = (size_t)(ok ? t : 0) * B + col;
+        r[u] = ok ? rewards[o] : 0.0f;
+        v[u] = (HAS_V && ok) ? values[o] : 0.0f;
+        d[u] = ok ? dones[o + B] : (uint8_t)0;
+        m[u] = (HAS_MASK && ok) ? mask[o] : (uint8_t)1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t_hi - u;
+        if (t >= 0) {
+          float rt, ad;
+          gae_step<HAS_V>(r[u], v[u], v_next, d[u], gamma, coef, g, rt, ad);
+          v_next = v[u];
+          const size_t o = (size_t)t * B + col;
+          adv[o] = ad;
+          ret[o] = rt;
+          if (HAS_STATS && m[u]) {
+            acc_a.add(ad);
+            acc_r.add(rt);
+          }
+        }
+      }
+    }
+  }
+  if (HAS_STATS) flush_stats(acc_a, acc_r, stats);
+}
+
+// x <- (x - mean) / (std + eps); stats = {n, sum, sumsq}; unbiased variance; skip when n == 0.
+__global__ void __launch_bounds__(256) normalize_kernel(float* __restrict__ x, const double* __restrict__ stats,
+                                                        int64_t n, float eps) {
+  const double cnt = stats[0];
+  if (cnt <= 0.0) return;
+  const double mean_d = stats[1] / cnt;
+  const double var_d = (stats[2] - stats[1] * mean_d) / (cnt - 1.0);  // n==1 -> 0/0 = NaN like torch.std
+  const float mean = (float)mean_d;
+  const float stdv = (float)sqrt(var_d > 0.0 || !(var_d == var_d) ? var_d : 0.0);
+  const float den = __fadd_rn(stdv, eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (int64_t k = i; k < n4; k += stride) {
+    float4 v = x4[k];
+    v.x = __fdiv_rn(__fsub_rn(v.x, mean), den);
+    v.y = __fdiv_rn(__fsub_rn(v.y, mean), den);
+    v.z = __fdiv_rn(__fsub_rn(v.z, mean), den);
+    v.w = __fdiv_rn(__fsub_rn(v.w, mean), den);
+    x4[k] = v;
+  }
+  for (int64_t k = n4 * 4 + i; k < n; k += stride) x[k] = __fdiv_rn(__fsub_rn(x[k], mean), den);
+}
+
+template <bool HAS_V, bool HAS_MASK, bool HAS_STATS>
+int launch_gae(const float* rewards, const float* values, const uint8_t* dones, const uint8_t* mask, float* adv,
+               float* ret, double* stats, int T, int B, float gamma, float coef, cudaStream_t st) {
+  const bool aligned = (B % 16 == 0) && ((reinterpret_cast<uintptr_t>(rewards) & 15) == 0) &&
+                       (!HAS_V || (reinterpret_cast<uintptr_t>(values) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(dones) & 15) == 0) &&
+                       (!HAS_MASK || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+  const int grid = (B + kW - 1) / kW;
+  if (aligned) {
+    CUtensorMap tm_r, tm_v, tm_d, tm_m;
+    int e = rb::encode_tmap_2d(&tm_r, rewards, 4, (uint64_t)T, (uint64_t)B, kR, kW);
+    if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kR, kW);
+    if (!e) e = rb::encode_tmap_2d(&tm_d, dones, 1, (uint64_t)T + 1, (uint64_t)B, kR, kW);
+    if (!e && HAS_MASK) e = rb::encode_tmap_2d(&tm_m, mask, 1, (uint64_t)T, (uint64_t)B, kR, kW);
+    if (!HAS_V) tm_v = tm_r;
+    if (!HAS_MASK) tm_m = tm_d;
+    if (!e) {
+      gae_tma_kernel<HAS_V, HAS_MASK, HAS_STATS>
+          <<<grid, 64, 0, st>>>(tm_r, tm_v, tm_d, tm_m, values, adv, ret, stats, T, B, gamma, coef);
+      RB_RETURN_LAUNCH();
+    }
+    // descriptor encode failed (e.g. driver entry point unavailable): use the generic kernel
+  }
+  gae_generic_kernel<HAS_V, HAS_MASK, HAS_STATS>
+      <<<grid, 32, 0, st>>>(rewards, values, dones, mask, adv, ret, stats, T, B, gamma, coef);
+  RB_RETURN_LAUNCH();
+}
+
+}  // namespace
+
+extern "C" int rb200_gae(const float* rewards, const float* values, const uint8_t* dones, const uint8_t* loss_mask,
+                         float* adv, float* ret, double* stats, int T, int B, double gamma, double gae_lambda,
+                         rb200_stream_t stream) {
+  if (!rewards || !dones || !adv || !ret) return RB200_E_NULL;
+  if (T <= 0 || B <= 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  if (!values) {  // critic-free: the reference forces gamma = lambda = 1 (advantages.py:61-64)
+    gamma = 1.0;
+    gae_lambda = 1.0;
+  }
+  const float gamma_f = (float)gamma;
+  const float coef_f = (float)(gamma * gae_lambda);  // product in double, then one rounding
+  if (stats) RB_CHECK_CUDA(cudaMemsetAsync(stats, 0, 6 * sizeof(double), st));
+#define RB_GAE(V, M, S) \
+  return launch_gae<V, M, S>(rewards, values, dones, loss_mask, adv, ret, stats, T, B, gamma_f, coef_f, st)
+  if (values) {
+    if (stats) {
+      if (loss_mask) RB_GAE(true, true, true);
+      RB_GAE(true, false, true);
+    }
+    RB_GAE(true, false, false);
+  } else {
+    if (stats) {
+      if (loss_mask) RB_GAE(false, true, true);
+      RB_GAE(false, false, true);
+    }
+    RB_GAE(false, false, false);
+  }
+#undef RB_GAE
+}
+
+extern "C" int rb200_normalize(float* x, const double* stats, int64_t n_elems, float eps, rb200_stream_t stream) {
+  if (!x || !stats) return RB200_E_NULL;
+  if (n_elems <= 0) return RB200_E_SHAPE;
+  int64_t blocks = (n_elems / 4 + 255) / 256;
+  const int64_t cap = (int64_t)rb::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  normalize_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, stats, n_elems, eps);
+  RB_RETURN_LAUNCH();
+}

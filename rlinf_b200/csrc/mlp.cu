@@ -1,0 +1,682 @@
+// K3 / K5: MLP policy + value head: forward, backward, rollout sampling.
+// Reference: MLPPolicy.default_forward / _generate_actions, rlinf/models/embodiment/mlp_policy/mlp_policy.py:202-293
+// (3x256 tanh backbone -> actor_mean; state-independent actor_logstd; Normal log_prob / entropy) and
+// ValueHead, rlinf/models/embodiment/modules/value_head.py:18-67 (3x256 tanh MLP -> value_dim, last layer
+// without bias); backward = what autograd derives from them.
+//
+// This translation unit holds the fp32 SIMT GEMM path (exact fp32 accumulation: parity reference for the
+// tensor-core path) plus the fused head kernels (mean/value heads + Normal log-prob/entropy epilogue, and
+// their backward).  Activations are kept as tanh outputs (tanh' = 1 - h^2), 6 x [n,256] floats.
+#include <curand_kernel.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 8, NT = 256;
+
+enum AMode { A_KCONTIG = 0, A_MCONTIG = 1 };  // A(m,k) stored [M,K] (k fastest) or [K,M] (m fastest)
+enum BMode { B_KCONTIG = 0, B_NCONTIG = 1 };  // B(k,n) stored [N,K] (k fastest) or [K,N] (n fastest)
+enum Epi { EPI_BIAS_TANH = 0, EPI_TANHGRAD = 1, EPI_ATOMIC = 2 };
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  const int64_t* a_rows;  // optional row gather for A (A_KCONTIG) or for B rows r (wgrad layer 1: B_NCONTIG rows)
+  const int64_t* b_rows;
+  const float* bias;  // [N]          (EPI_BIAS_TANH)
+  const float* aux;   // [M, ldaux]   (EPI_TANHGRAD: previous activation h, out = acc * (1 - h^2))
+  int64_t M;          // rows of C; for the wgrad form this is N_out and K is the (huge) reduction over samples
+  int N, lda, ldb, ldc, ldaux;
+  int64_t K;
+  int64_t k_per_split;  // reduction range per blockIdx.z
+};
+
+__device__ __forceinline__ float4 ld4(const float* p, bool vec, int valid) {
+  // loads p[0..3]; `valid` = number of in-range elements (0..4); vec => 16-byte aligned & all valid
+  if (vec) return *reinterpret_cast<const float4*>(p);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid > 0) r.x = p[0];
+  if (valid > 1) r.y = p[1];
+  if (valid > 2) r.z = p[2];
+  if (valid > 3) r.w = p[3];
+  return r;
+}
+
+template <int AM, int BMODE, int EPI>
+__global__ void __launch_bounds__(NT) sgemm_kernel(GemmArgs p) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // ---- tile load plans (one float4 per thread per tile) ----
+  // KCONTIG: 128 rows x 8 k -> thread: row = tid/2, kq = (tid&1)*4 ; stored transposed
+  // M/N CONTIG: 8 k x 128 cols -> thread: kk = tid/32, cq = (tid&31)*4 ; stored directly
+  const int a_row = (AM == A_KCONTIG) ? (tid >> 1) : ((tid & 31) * 4);
+  const int a_k = (AM == A_KCONTIG) ? ((tid & 1) * 4) : (tid >> 5);
+  const int b_col = (BMODE == B_KCONTIG) ? (tid >> 1) : ((tid & 31) * 4);
+  const int b_k = (BMODE == B_KCONTIG) ? ((tid & 1) * 4) : (tid >> 5);
+
+  const bool a_vec_ok = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+  const bool b_vec_ok = ((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
+
+  const float* a_ptr = nullptr;  // A_KCONTIG: row base pointer (fixed over k)
+  bool a_row_ok = false;
+  if (AM == A_KCONTIG) {
+    const int64_t m = m0 + a_row;
+    a_row_ok = m < p.M;
+    if (a_row_ok) {
+      const int64_t src = p.a_rows ? p.a_rows[m] : m;
+      a_ptr = p.A + src * p.lda;
+    }
+  }
+  const float* b_ptr = nullptr;
+  bool b_col_ok = false;
+  if (BMODE == B_KCONTIG) {
+    const int n = n0 + b_col;
+    b_col_ok = n < p.N;
+    if (b_col_ok) b_ptr = p.B + (int64_t)n * p.ldb;
+  }
+
+  auto load_a = [&](int64_t k0) -> float4 {
+    if (AM == A_KCONTIG) {
+      const int64_t k = k0 + a_k;
+      if (!a_row_ok || k >= kend) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int valid = (int)((kend - k) < 4 ? (kend - k) : 4);
+      return ld4(a_ptr + k, a_vec_ok && valid == 4, valid);
+    } else {  // A(m,k) = A[k*lda + m], m fastest. k is the reduction index (sample row for wgrad)
+      const int64_t k = k0 + a_k;
+      const int64_t m = m0 + a_row;
+      if (k >= kend || m >= p.M) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t src = p.a_rows ? p.a_rows[k] : k;
+      const int valid = (int)((p.M - m) < 4 ? (p.M - m) : 4);
+      return ld4(p.A + src * p.lda + m, a_vec_ok && valid == 4, valid);
+    }
+  };
+  auto load_b = [&](int64_t k0) -> float4 {
+    if (BMODE == B_KCONTIG) {
+      const int64_t k = k0 + b_k;
+      if (!b_col_ok || k >= kend) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int valid = (int)((kend - k) < 4 ? (kend - k) : 4);
+      return ld4(b_ptr + k, b_vec_ok && valid == 4, valid);
+    } else {  // B(k,n) = B[k*ldb + n]
+      const int64_t k = k0 + b_k;
+      const int n = n0 + b_col;
+      if (k >= kend || n >= p.N) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t src = p.b_rows ? p.b_rows[k] : k;
+      const int valid = (p.N - n) < 4 ? (p.N - n) : 4;
+      return ld4(p.B + src * p.ldb + n, b_vec_ok && valid == 4, valid);
+    }
+  };
+  auto store_a = [&](int buf, float4 v) {
+    if (AM == A_KCONTIG) {
+      As[buf][a_k + 0][a_row] = v.x;
+      As[buf][a_k + 1][a_row] = v.y;
+      As[buf][a_k + 2][a_row] = v.z;
+      As[buf][a_k + 3][a_row] = v.w;
+    } else {
+      *reinterpret_cast<float4*>(&As[buf][a_k][a_row]) = v;
+    }
+  };
+  auto store_b = [&](int buf, float4 v) {
+    if (BMODE == B_KCONTIG) {
+      Bs[buf][b_k + 0][b_col] = v.x;
+      Bs[buf][b_k + 1][b_col] = v.y;
+      Bs[buf][b_k + 2][b_col] = v.z;
+      Bs[buf][b_k + 3][b_col] = v.w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col]) = v;
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra = load_a(kbeg), rb_ = load_b(kbeg);
+  store_a(0, ra);
+  store_b(0, rb_);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool has_next = (k0 + BK) < kend;
+    if (has_next) {
+      ra = load_a(k0 + BK);
+      rb_ = load_b(k0 + BK);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_a(buf ^ 1, ra);
+      store_b(buf ^ 1, rb_);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + (jh == 0 ? tx * 4 : 64 + tx * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j >= p.N) continue;
+        float v = acc[i][jh * 4 + j];
+        float* dst = p.C + m * p.ldc + n + j;
+        if (EPI == EPI_BIAS_TANH) {
+          v = tanhf(v + p.bias[n + j]);
+          *dst = v;
+        } else if (EPI == EPI_TANHGRAD) {
+          const float h = p.aux[m * p.ldaux + n + j];
+          *dst = v * (1.0f - h * h);
+        } else {
+          atomicAdd(dst, v);
+        }
+      }
+    }
+  }
+}
+
+template <int AM, int BMODE, int EPI>
+int launch_gemm(const GemmArgs& p, int splits, cudaStream_t st) {
+  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
+  sgemm_kernel<AM, BMODE, EPI><<<grid, NT, 0, st>>>(p);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+// out[n] += sum_m Z[m][n]   (bias gradients); Z is [M, N] with N <= 1024
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, float* __restrict__ out, int64_t M,
+                                                     int N, int64_t rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+      s0 += Z[r * N + n];
+      s1 += Z[(r + 1) * N + n];
+      s2 += Z[(r + 2) * N + n];
+      s3 += Z[(r + 3) * N + n];
+    }
+    for (; r < r1; ++r) s0 += Z[r * N + n];
+    atomicAdd(&out[n], (s0 + s1) + (s2 + s3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused heads.  One warp per sample row; H = 256 hidden units -> 8 per lane (two float4).
+// ------------------------------------------------------------------------------------------------
+constexpr int kH = 256;
+constexpr int kMaxAct = 32;
+constexpr int kMaxVal = 8;
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
+
+struct HeadFwdArgs {
+  const float* h3;      // [n,256] backbone features
+  const float* g3;      // [n,256] value features (may be null -> no values)
+  const float* mw;      // [act,256]
+  const float* mb;      // [act]
+  const float* logstd;  // [act]
+  const float* vw3;     // [vdim,256]
+  const float* action;  // [rows,act] given actions (gathered by idx) or null in sample mode
+  const int64_t* idx;
+  const float* noise;   // sample mode: [n,act] N(0,1) draws or null -> Philox
+  uint64_t seed, offset;
+  int sample_mode;
+  float* mean_out;     // [n,act] or null
+  float* action_out;   // sample mode
+  float* logprobs;     // [n,act]
+  float* entropy;      // [n,act] or null
+  float* values;       // [n,vdim] or null
+  int64_t n;
+  int act, vdim;
+};
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
+  extern __shared__ float sm[];  // mw [act][256] | vw3 [vdim][256]
+  float* s_mw = sm;
+  float* s_vw = sm + p.act * kH;
+  for (int i = threadIdx.x; i < p.act * kH; i += blockDim.x) s_mw[i] = p.mw[i];
+  if (p.g3 && p.values)
+    for (int i = threadIdx.x; i < p.vdim * kH; i += blockDim.x) s_vw[i] = p.vw3[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
+    const float4 h0 = *reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4);
+    const float4 h1 = *reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4);
+    float my_mean = 0.f;
+    for (int a = 0; a < p.act; ++a) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_mw + a * kH + lane * 4);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_mw + a * kH + 128 + lane * 4);
+      float s = h0.x * w0.x + h0.y * w0.y + h0.z * w0.z + h0.w * w0.w + h1.x * w1.x + h1.y * w1.y + h1.z * w1.z +
+                h1.w * w1.w;
+      s = rb::warp_sum(s);
+      if (lane == a) my_mean = s + p.mb[a];
+    }
+    if (lane < p.act) {
+      const float ls = p.logstd[lane];
+      const float sd = expf(ls);
+      float x;
+      if (p.sample_mode) {
+        float z;
+        if (p.noise) {
+          z = p.noise[row * p.act + lane];
+        } else {
+          curandStatePhilox4_32_10_t st;
+          curand_init(p.seed, (unsigned long long)(row * p.act + lane), p.offset, &st);
+          z = curand_normal(&st);
+        }
+        x = my_mean + sd * z;
+        p.action_out[row * p.act + lane] = x;
+      } else {
+        const int64_t src = p.idx ? p.idx[row] : row;
+        x = p.action[src * p.act + lane];
+      }
+      // torch.distributions.Normal.log_prob: -((x-mu)^2)/(2 var) - log(sd) - log(sqrt(2 pi))
+      const float d = x - my_mean;
+      const float var = sd * sd;
+      p.logprobs[row * p.act + lane] = -(d * d) / (2.0f * var) - logf(sd) - kHalfLog2Pi;
+      if (p.entropy) p.entropy[row * p.act + lane] = 0.5f + kHalfLog2Pi + logf(sd);
+      if (p.mean_out) p.mean_out[row * p.act + lane] = my_mean;
+    }
+    if (p.g3 && p.values) {
+      const float4 g0 = *reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4);
+      const float4 g1 = *reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4);
+      for (int c = 0; c < p.vdim; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_vw + c * kH + lane * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_vw + c * kH + 128 + lane * 4);
+        float s = g0.x * w0.x + g0.y * w0.y + g0.z * w0.z + g0.w * w0.w + g1.x * w1.x + g1.y * w1.y + g1.z * w1.z +
+                  g1.w * w1.w;
+        s = rb::warp_sum(s);
+        if (lane == 0) p.values[row * p.vdim + c] = s;
+      }
+    }
+  }
+}
+
+struct HeadBwdArgs {
+  const float* h3;
+  const float* g3;
+  const float* mean;    // [n,act] saved by forward
+  const float* mw;
+  const float* logstd;
+  const float* vw3;
+  const float* action;
+  const int64_t* idx;
+  const float* d_logprobs;  // [n,act]
+  const float* d_entropy;   // [n,act] or null
+  const float* d_values;    // [n,vdim] or null
+  float* dz3;               // [n,256] out: grad wrt backbone layer-3 pre-activation
+  float* dy3;               // [n,256] out: grad wrt value layer-3 pre-activation (if d_values)
+  float* g_mw;              // [act,256] +=
+  float* g_mb;              // [act] +=
+  float* g_logstd;          // [act] +=
+  float* g_vw3;             // [vdim,256] +=
+  int64_t n;
+  int act, vdim;
+};
+
+// REG = true: act <= 8 and vdim <= 2 -> weight-gradient partials live in registers for the whole row loop
+// (one shared-memory flush per warp); REG = false: generic path through shared-memory atomics.
+template <bool REG>
+__global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
+  extern __shared__ float sm[];
+  // layout: mw [act][256] | vw [vdim][256] | acc_mw [act][256] | acc_vw [vdim][256] | acc_mb[32] | acc_ls[32]
+  float* s_mw = sm;
+  float* s_vw = s_mw + p.act * kH;
+  float* a_mw = s_vw + p.vdim * kH;
+  float* a_vw = a_mw + p.act * kH;
+  float* a_mb = a_vw + p.vdim * kH;
+  float* a_ls = a_mb + 32;
+  const bool has_v = p.d_values != nullptr;
+  for (int i = threadIdx.x; i < p.act * kH; i += blockDim.x) {
+    s_mw[i] = p.mw[i];
+    a_mw[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < p.vdim * kH; i += blockDim.x) {
+    s_vw[i] = has_v ? p.vw3[i] : 0.f;
+    a_vw[i] = 0.f;
+  }
+  if (threadIdx.x < 64) a_mb[threadIdx.x] = 0.f;  // a_mb and a_ls are contiguous
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float rm[REG ? 8 : 1][8], rv[REG ? 2 : 1][8];
+#pragma unroll
+  for (int a = 0; a < (REG ? 8 : 1); ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rm[a][j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < (REG ? 2 : 1); ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rv[c][j] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
+    const float4 h0 = *reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4);
+    const float4 h1 = *reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4);
+    float dmu = 0.f;
+    if (lane < p.act) {
+      const int64_t src = p.idx ? p.idx[row] : row;
+      const float x = p.action[src * p.act + lane];
+      const float mu = p.mean[row * p.act + lane];
+      const float sd = expf(p.logstd[lane]);
+      const float var = sd * sd;
+      const float dlp = p.d_logprobs[row * p.act + lane];
+      const float d = x - mu;
+      dmu = dlp * d / var;
+      float dls = dlp * (d * d / var - 1.0f);
+      if (p.d_entropy) dls += p.d_entropy[row * p.act + lane];
+      atomicAdd(&a_mb[lane], dmu);
+      atomicAdd(&a_ls[lane], dls);
+    }
+    float4 dh0 = make_float4(0.f, 0.f, 0.f, 0.f), dh1 = dh0;
+#pragma unroll
+    for (int a = 0; a < (REG ? 8 : kMaxAct); ++a) {
+      if (a >= p.act) break;
+      const float g = __shfl_sync(0xffffffffu, dmu, a);
+      const float4 w0 = *reinterpret_cast<const float4*>(s_mw + a * kH + lane * 4);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_mw + a * kH + 128 + lane * 4);
+      dh0.x += g * w0.x; dh0.y += g * w0.y; dh0.z += g * w0.z; dh0.w += g * w0.w;
+      dh1.x += g * w1.x; dh1.y += g * w1.y; dh1.z += g * w1.z; dh1.w += g * w1.w;
+      if (REG) {
+        const int ar = a < 8 ? a : 0;
+        rm[ar][0] += g * h0.x; rm[ar][1] += g * h0.y; rm[ar][2] += g * h0.z; rm[ar][3] += g * h0.w;
+        rm[ar][4] += g * h1.x; rm[ar][5] += g * h1.y; rm[ar][6] += g * h1.z; rm[ar][7] += g * h1.w;
+        continue;
+      }
+      float* am = a_mw + a * kH;
+      atomicAdd(&am[lane * 4 + 0], g * h0.x); atomicAdd(&am[lane * 4 + 1], g * h0.y);
+      atomicAdd(&am[lane * 4 + 2], g * h0.z); atomicAdd(&am[lane * 4 + 3], g * h0.w);
+      atomicAdd(&am[128 + lane * 4 + 0], g * h1.x); atomicAdd(&am[128 + lane * 4 + 1], g * h1.y);
+      atomicAdd(&am[128 + lane * 4 + 2], g * h1.z); atomicAdd(&am[128 + lane * 4 + 3], g * h1.w);
+    }
+    float4 o0, o1;
+    o0.x = dh0.x * (1.f - h0.x * h0.x); o0.y = dh0.y * (1.f - h0.y * h0.y);
+    o0.z = dh0.z * (1.f - h0.z * h0.z); o0.w = dh0.w * (1.f - h0.w * h0.w);
+    o1.x = dh1.x * (1.f - h1.x * h1.x); o1.y = dh1.y * (1.f - h1.y * h1.y);
+    o1.z = dh1.z * (1.f - h1.z * h1.z); o1.w = dh1.w * (1.f - h1.w * h1.w);
+    *reinterpret_cast<float4*>(p.dz3 + row * kH + lane * 4) = o0;
+    *reinterpret_cast<float4*>(p.dz3 + row * kH + 128 + lane * 4) = o1;
+
+    if (has_v) {
+      const float4 g0 = *reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4);
+      const float4 g1 = *reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4);
+      float4 dg0 = make_float4(0.f, 0.f, 0.f, 0.f), dg1 = dg0;
+#pragma unroll
+      for (int c = 0; c < (REG ? 2 : kMaxVal); ++c) {
+        if (c >= p.vdim) break;
+        const float g = p.d_values[row * p.vdim + c];
+        const float4 w0 = *reinterpret_cast<const float4*>(s_vw + c * kH + lane * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_vw + c * kH + 128 + lane * 4);
+        dg0.x += g * w0.x; dg0.y += g * w0.y; dg0.z += g * w0.z; dg0.w += g * w0.w;
+        dg1.x += g * w1.x; dg1.y += g * w1.y; dg1.z += g * w1.z; dg1.w += g * w1.w;
+        if (REG) {
+          const int cr = c < 2 ? c : 0;
+          rv[cr][0] += g * g0.x; rv[cr][1] += g * g0.y; rv[cr][2] += g * g0.z; rv[cr][3] += g * g0.w;
+          rv[cr][4] += g * g1.x; rv[cr][5] += g * g1.y; rv[cr][6] += g * g1.z; rv[cr][7] += g * g1.w;
+          continue;
+        }
+        float* av = a_vw + c * kH;
+        atomicAdd(&av[lane * 4 + 0], g * g0.x); atomicAdd(&av[lane * 4 + 1], g * g0.y);
+        atomicAdd(&av[lane * 4 + 2], g * g0.z); atomicAdd(&av[lane * 4 + 3], g * g0.w);
+        atomicAdd(&av[128 + lane * 4 + 0], g * g1.x); atomicAdd(&av[128 + lane * 4 + 1], g * g1.y);
+        atomicAdd(&av[128 + lane * 4 + 2], g * g1.z); atomicAdd(&av[128 + lane * 4 + 3], g * g1.w);
+      }
+      float4 q0, q1;
+      q0.x = dg0.x * (1.f - g0.x * g0.x); q0.y = dg0.y * (1.f - g0.y * g0.y);
+      q0.z = dg0.z * (1.f - g0.z * g0.z); q0.w = dg0.w * (1.f - g0.w * g0.w);
+      q1.x = dg1.x * (1.f - g1.x * g1.x); q1.y = dg1.y * (1.f - g1.y * g1.y);
+      q1.z = dg1.z * (1.f - g1.z * g1.z); q1.w = dg1.w * (1.f - g1.w * g1.w);
+      *reinterpret_cast<float4*>(p.dy3 + row * kH + lane * 4) = q0;
+      *reinterpret_cast<float4*>(p.dy3 + row * kH + 128 + lane * 4) = q1;
+    }
+  }
+  if (REG) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a >= p.act) break;
+      float* am = a_mw + a * kH;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&am[lane * 4 + j], rm[a][j]);
+        atomicAdd(&am[128 + lane * 4 + j], rm[a][4 + j]);
+      }
+    }
+    if (has_v) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c >= p.vdim) break;
+        float* av = a_vw + c * kH;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(&av[lane * 4 + j], rv[c][j]);
+          atomicAdd(&av[128 + lane * 4 + j], rv[c][4 + j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.act * kH; i += blockDim.x)
+    if (a_mw[i] != 0.f) atomicAdd(&p.g_mw[i], a_mw[i]);
+  if (has_v)
+    for (int i = threadIdx.x; i < p.vdim * kH; i += blockDim.x)
+      if (a_vw[i] != 0.f) atomicAdd(&p.g_vw3[i], a_vw[i]);
+  if (threadIdx.x < p.act) {
+    atomicAdd(&p.g_mb[threadIdx.x], a_mb[threadIdx.x]);
+    atomicAdd(&p.g_logstd[threadIdx.x], a_ls[threadIdx.x]);
+  }
+}
+
+int head_grid(int64_t n) {
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = (int64_t)rb::sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// three hidden layers of one tower: X -> H1 -> H2 -> H3
+int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const float* w2, const float* b2, float* H1, float* H2, float* H3,
+                  cudaStream_t st) {
+  GemmArgs g{};
+  g.M = n; g.N = kH; g.ldc = kH; g.k_per_split = 1 << 30;
+  g.A = X; g.lda = in_dim; g.a_rows = idx; g.B = w0; g.ldb = in_dim; g.K = in_dim; g.bias = b0; g.C = H1;
+  int e = launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
+  if (e) return e;
+  g.A = H1; g.lda = kH; g.a_rows = nullptr; g.B = w1; g.ldb = kH; g.K = kH; g.bias = b1; g.C = H2;
+  e = launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
+  if (e) return e;
+  g.A = H2; g.B = w2; g.bias = b2; g.C = H3;
+  return launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
+}
+
+// backward through the three hidden layers of one tower, given dZ3 (grad wrt layer-3 pre-activation).
+// buffers: dZ3 is overwritten-free; tmpA/tmpB are [n,256] scratch.
+int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, const float* w1, const float* w2,
+                   const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB, float* g_w0,
+                   float* g_b0, float* g_w1, float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
+  const int64_t rows_per_split = 4096;
+  const int splits = (int)((n + rows_per_split - 1) / rows_per_split);
+  const int64_t cs_rows = 1024;
+  const int cs_blocks = (int)((n + cs_rows - 1) / cs_rows);
+  int e;
+  auto wgrad = [&](const float* dZ, const float* Hin, const int64_t* in_rows, int in_ld, float* gw, float* gb) -> int {
+    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
+    GemmArgs g{};
+    g.A = dZ; g.lda = kH; g.B = Hin; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw; g.ldc = in_ld;
+    g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
+    int ee = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(g, splits, st);
+    if (ee) return ee;
+    colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, gb, n, kH, cs_rows);
+    cudaError_t ce = cudaPeekAtLastError();
+    return ce == cudaSuccess ? 0 : (int)ce;
+  };
+  auto dgrad = [&](const float* dZ, const float* W, const float* Hprev, float* out) -> int {
+    // out[n,256] = (dZ [n,256] . W [256,256]) * (1 - Hprev^2)
+    GemmArgs g{};
+    g.A = dZ; g.lda = kH; g.B = W; g.ldb = kH; g.C = out; g.ldc = kH; g.aux = Hprev; g.ldaux = kH;
+    g.M = n; g.N = kH; g.K = kH; g.k_per_split = 1 << 30;
+    return launch_gemm<A_KCONTIG, B_NCONTIG, EPI_TANHGRAD>(g, 1, st);
+  };
+  if ((e = wgrad(dZ3, H2, nullptr, kH, g_w2, g_b2))) return e;
+  if ((e = dgrad(dZ3, w2, H2, tmpA))) return e;        // dZ2
+  if ((e = wgrad(tmpA, H1, nullptr, kH, g_w1, g_b1))) return e;
+  if ((e = dgrad(tmpA, w1, H1, tmpB))) return e;        // dZ1
+  return wgrad(tmpB, X, idx, in_dim, g_w0, g_b0);
+}
+
+}  // namespace
+
+extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_dim, int value_dim, int hidden) {
+  if (!L) return RB200_E_NULL;
+  if (obs_dim <= 0 || act_dim <= 0 || value_dim < 0) return RB200_E_SHAPE;
+  if (hidden != kH || act_dim > kMaxAct || value_dim > kMaxVal) return RB200_E_UNSUPPORTED;
+  L->obs_dim = obs_dim; L->act_dim = act_dim; L->value_dim = value_dim; L->hidden = hidden;
+  int64_t o = 0;
+  auto take = [&](int64_t n) { const int64_t at = o; o += n; return at; };
+  // named_parameters() order of the reference MLPPolicy: own Parameter first, then children in construction
+  // order (value_head, backbone, actor_mean) - mlp_policy.py:28-105
+  L->logstd = take(act_dim);
+  L->vw0 = take((int64_t)hidden * obs_dim); L->vb0 = take(hidden);
+  L->vw1 = take((int64_t)hidden * hidden); L->vb1 = take(hidden);
+  L->vw2 = take((int64_t)hidden * hidden); L->vb2 = take(hidden);
+  L->vw3 = take((int64_t)value_dim * hidden);
+  L->bw0 = take((int64_t)hidden * obs_dim); L->bb0 = take(hidden);
+  L->bw1 = take((int64_t)hidden * hidden); L->bb1 = take(hidden);
+  L->bw2 = take((int64_t)hidden * hidden); L->bb2 = take(hidden);
+  L->mw = take((int64_t)act_dim * hidden); L->mb = take(act_dim);
+  L->total = o;
+  return RB200_OK;
+}
+
+// acts layout (floats): H1 H2 H3 G1 G2 G3 (each n*256) | mean (n*act)
+extern "C" int64_t rb200_mlp_fwd_scratch_floats(const rb200_mlp_layout* L, int64_t n) {
+  if (!L || n <= 0) return 0;
+  return 6 * n * kH + n * L->act_dim + 64;
+}
+
+static int check_layout(const rb200_mlp_layout* L) {
+  if (!L) return RB200_E_NULL;
+  if (L->hidden != kH || L->act_dim <= 0 || L->act_dim > kMaxAct || L->value_dim < 0 || L->value_dim > kMaxVal)
+    return RB200_E_UNSUPPORTED;
+  return RB200_OK;
+}
+
+extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* states,
+                                 const float* action, const int64_t* idx, int64_t n, float* logprobs, float* entropy,
+                                 float* values, float* acts, rb200_stream_t stream) {
+  int e = check_layout(L);
+  if (e) return e;
+  if (!params || !states || !action || !logprobs || !acts) return RB200_E_NULL;
+  if (n <= 0) return RB200_E_SHAPE;
+  if (values && L->value_dim == 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  float *H1 = acts, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH, *G3 = G2 + n * kH;
+  float* mean = G3 + n * kH;
+  const float* P = params;
+  if ((e = tower_forward(states, idx, n, L->obs_dim, P + L->bw0, P + L->bb0, P + L->bw1, P + L->bb1, P + L->bw2,
+                         P + L->bb2, H1, H2, H3, st)))
+    return e;
+  if (values && (e = tower_forward(states, idx, n, L->obs_dim, P + L->vw0, P + L->vb0, P + L->vw1, P + L->vb1,
+                                   P + L->vw2, P + L->vb2, G1, G2, G3, st)))
+    return e;
+  HeadFwdArgs h{};
+  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb; h.logstd = P + L->logstd;
+  h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.sample_mode = 0; h.mean_out = mean; h.logprobs = logprobs;
+  h.entropy = entropy; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  const size_t smem = sizeof(float) * (size_t)(L->act_dim + L->value_dim) * kH;
+  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h);
+  RB_RETURN_LAUNCH();
+}
+
+extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* states,
+                                  const float* action, const int64_t* idx, int64_t n, const float* d_logprobs,
+                                  const float* d_entropy, const float* d_values, const float* acts, float* work,
+                                  float* grads, rb200_stream_t stream) {
+  int e = check_layout(L);
+  if (e) return e;
+  if (!params || !states || !action || !d_logprobs || !acts || !work || !grads) return RB200_E_NULL;
+  if (n <= 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  const float *H1 = acts, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH,
+              *G3 = G2 + n * kH;
+  const float* mean = G3 + n * kH;
+  float *dZ3 = work, *tA = dZ3 + n * kH, *tB = tA + n * kH, *dY3 = tB + n * kH, *uA = dY3 + n * kH, *uB = uA + n * kH;
+  const float* P = params;
+  float* G = grads;
+  HeadBwdArgs h{};
+  h.h3 = H3; h.g3 = G3; h.mean = mean; h.mw = P + L->mw; h.logstd = P + L->logstd; h.vw3 = P + L->vw3;
+  h.action = action; h.idx = idx; h.d_logprobs = d_logprobs; h.d_entropy = d_entropy; h.d_values = d_values;
+  h.dz3 = dZ3; h.dy3 = dY3; h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
+  h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  const size_t smem = sizeof(float) * ((size_t)2 * (L->act_dim + L->value_dim) * kH + 64);
+  const bool reg = L->act_dim <= 8 && L->value_dim <= 2;
+  if (smem > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(head_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  if (reg)
+    head_bwd_kernel<true><<<head_grid(n), 256, smem, st>>>(h);
+  else
+    head_bwd_kernel<false><<<head_grid(n), 256, smem, st>>>(h);
+  {
+    cudaError_t ce = cudaPeekAtLastError();
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  if ((e = tower_backward(states, idx, n, L->obs_dim, P + L->bw1, P + L->bw2, H1, H2, dZ3, tA, tB, G + L->bw0,
+                          G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
+    return e;
+  if (d_values &&
+      (e = tower_backward(states, idx, n, L->obs_dim, P + L->vw1, P + L->vw2, G1, G2, dY3, uA, uB, G + L->vw0,
+                          G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
+    return e;
+  return RB200_OK;
+}
+
+extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* states,
+                                const float* noise, uint64_t seed, uint64_t offset, int64_t n, float* action,
+                                float* logprobs, float* values, float* work, rb200_stream_t stream) {
+  int e = check_layout(L);
+  if (e) return e;
+  if (!params || !states || !action || !logprobs || !work) return RB200_E_NULL;
+  if (n <= 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  float *H1 = work, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH, *G3 = G2 + n * kH;
+  const float* P = params;
+  if ((e = tower_forward(states, nullptr, n, L->obs_dim, P + L->bw0, P + L->bb0, P + L->bw1, P + L->bb1, P + L->bw2,
+                         P + L->bb2, H1, H2, H3, st)))
+    return e;
+  if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, P + L->vw0, P + L->vb0, P + L->vw1, P + L->vb1,
+                                   P + L->vw2, P + L->vb2, G1, G2, G3, st)))
+    return e;
+  HeadFwdArgs h{};
+  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb; h.logstd = P + L->logstd;
+  h.vw3 = P + L->vw3; h.noise = noise; h.seed = seed; h.offset = offset; h.sample_mode = 1; h.action_out = action;
+  h.logprobs = logprobs; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  const size_t smem = sizeof(float) * (size_t)(L->act_dim + L->value_dim) * kH;
+  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h);
+  RB_RETURN_LAUNCH();
+}

@@ -1,0 +1,170 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point).
+
+All compute happens in librlinf_b200.so on the current CUDA stream; these wrappers only allocate
+outputs (torch.empty) and translate pointers.  Inputs on the host are copied to the device first.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def loss_mask(dones: torch.Tensor):
+    """compute_loss_mask (rlinf/utils/metric_utils.py:516-537). dones bool [nc+1,B,C] ->
+    (mask bool [nc,B,C], mask_sum int64 [nc,B,C] expanded view of the per-env count)."""
+    lib = L.load()
+    if dones.dim() != 3:
+        raise ValueError(f"dones must be [n_chunk_steps+1, bsz, num_action_chunks], got {tuple(dones.shape)}")
+    d = L.as_u8(L.to_device(dones))
+    ncp1, B, Cc = d.shape
+    mask = torch.empty((ncp1 - 1, B, Cc), dtype=torch.uint8, device=d.device)
+    msum = torch.empty((B,), dtype=torch.int64, device=d.device)
+    L.check(lib.rb200_loss_mask(L.ptr(d), L.ptr(mask), L.ptr(msum), ncp1 - 1, B, Cc, L.stream_ptr()), "loss_mask")
+    return mask.view(torch.bool), msum.view(1, B, 1).expand(ncp1 - 1, B, Cc)
+
+
+def gae(rewards, values, dones, gamma, gae_lambda, loss_mask=None, want_stats=False):
+    """Un-normalised GAE on step-major [T,B] tensors -> (adv, ret, stats|None)."""
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32)
+    dev = r.device
+    v = L.to_device(values, dev, torch.float32)
+    d = L.as_u8(L.to_device(dones, dev))
+    m = L.as_u8(L.to_device(loss_mask, dev))
+    T, B = r.shape
+    if d.shape != (T + 1, B):
+        raise ValueError(f"dones must be [T+1,B]=({T + 1},{B}), got {tuple(d.shape)}")
+    if v is not None and v.shape != (T + 1, B):
+        raise ValueError(f"values must be [T+1,B]=({T + 1},{B}), got {tuple(v.shape)}")
+    if m is not None and m.shape != (T, B):
+        raise ValueError(f"loss_mask must be [T,B]=({T},{B}), got {tuple(m.shape)}")
+    adv = torch.empty_like(r)
+    ret = torch.empty_like(r)
+    stats = torch.empty(6, dtype=torch.float64, device=dev) if want_stats else None
+    L.check(lib.rb200_gae(L.ptr(r), L.ptr(v), L.ptr(d), L.ptr(m), L.ptr(adv), L.ptr(ret), L.ptr(stats), T, B,
+                          float(gamma), float(gae_lambda), L.stream_ptr()), "gae")
+    return adv, ret, stats
+
+
+def normalize_(x: torch.Tensor, stats: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """In-place (x-mean)/(std+eps) from {n,sum,sumsq} (safe_normalize's apply half)."""
+    lib = L.load()
+    L.check(lib.rb200_normalize(L.ptr(x), L.ptr(stats), x.numel(), float(eps), L.stream_ptr()), "normalize")
+    return x
+
+
+def grpo_scores(rewards, dones) -> torch.Tensor:
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32)
+    d = L.as_u8(L.to_device(dones, r.device))
+    T, B = r.shape
+    s = torch.empty((B,), dtype=torch.float32, device=r.device)
+    L.check(lib.rb200_grpo_scores(L.ptr(r), L.ptr(d), L.ptr(s), T, B, L.stream_ptr()), "grpo_scores")
+    return s
+
+
+def grpo_advantages(scores, loss_mask, T, group_size, eps=1e-6) -> torch.Tensor:
+    lib = L.load()
+    s = L.to_device(scores, dtype=torch.float32).reshape(-1)
+    m = L.as_u8(L.to_device(loss_mask, s.device))
+    B = s.numel()
+    adv = torch.empty((T, B), dtype=torch.float32, device=s.device)
+    L.check(lib.rb200_grpo_advantages(L.ptr(s), L.ptr(m), L.ptr(adv), T, B, int(group_size), float(eps),
+                                      L.stream_ptr()), "grpo_advantages")
+    return adv
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """dst = src.reshape(N, -1)[idx] with the trailing shape kept (bit-exact row gather)."""
+    lib = L.load()
+    s = L.to_device(src)
+    i = L.to_device(idx, s.device, torch.int64)
+    n_src = s.shape[0]
+    row_bytes = s[0].numel() * s.element_size() if n_src > 0 else 0
+    out = torch.empty((i.numel(), *s.shape[1:]), dtype=s.dtype, device=s.device)
+    if i.numel() == 0 or row_bytes == 0:
+        return out
+    L.check(lib.rb200_gather_rows(L.ptr(s), L.ptr(i), L.ptr(out), i.numel(), n_src, row_bytes, L.stream_ptr()),
+            "gather_rows")
+    return out
+
+
+def ppo_loss(*, logprobs, old_logprobs, advantages, C_chunks, A_dim, logprob_type, values=None, returns=None,
+             prev_values=None, loss_mask=None, loss_mask_sum=None, mask_sum_row_mod=0, idx=None, entropy=None,
+             adv_stats=None, adv_norm_eps=1e-5, clip_ratio_low=0.2, clip_ratio_high=0.2, clip_ratio_c=None,
+             clip_log_ratio_min=None, clip_log_ratio_max=None, value_clip=0.0, huber_delta=0.0,
+             max_episode_steps=None, critic_warmup=False, entropy_bonus=0.0, loss_scale=1.0, want_grads=True):
+    """One fused launch group. Returns (loss[1], metrics[24], d_logprobs|None, d_values|None, d_entropy|None)."""
+    lib = L.load()
+    dev = logprobs.device
+    bsz = logprobs.shape[0]
+    with_critic = values is not None
+    lp = logprobs.contiguous()
+    a = L.PpoArgs()
+    a.bsz, a.C, a.A = bsz, int(C_chunks), int(A_dim)
+    a.logprob_type = L.LOGPROB_TYPES[logprob_type] if isinstance(logprob_type, str) else int(logprob_type)
+    a.with_critic = 1 if with_critic else 0
+    keep = [lp]
+
+    def P(t, dtype=None):
+        if t is None:
+            return None
+        t = L.to_device(t, dev, dtype)
+        keep.append(t)
+        return L.ptr(t)
+
+    a.logprobs = L.ptr(lp)
+    a.values = P(values, torch.float32)
+    a.entropy = P(entropy, torch.float32)
+    a.idx = P(idx, torch.int64)
+    a.old_logprobs = P(old_logprobs, torch.float32)
+    a.advantages = P(advantages, torch.float32)
+    a.returns = P(returns, torch.float32)
+    a.prev_values = P(prev_values, torch.float32)
+    a.loss_mask = P(L.as_u8(loss_mask) if loss_mask is not None else None)
+    a.loss_mask_sum = P(loss_mask_sum, torch.int64)
+    a.mask_sum_row_mod = int(mask_sum_row_mod)
+    a.adv_stats = P(adv_stats, torch.float64)
+    a.adv_norm_eps = float(adv_norm_eps)
+    a.clip_ratio_low, a.clip_ratio_high = float(clip_ratio_low), float(clip_ratio_high)
+    a.clip_ratio_c = float(clip_ratio_c) if clip_ratio_c is not None else 0.0
+    if clip_ratio_c is not None and not clip_ratio_c > 1.0:
+        raise AssertionError("clip_ratio_c must be greater than 1.0")  # losses.py:260
+    a.has_clip_log_ratio_min = int(clip_log_ratio_min is not None)
+    a.has_clip_log_ratio_max = int(clip_log_ratio_max is not None)
+    a.clip_log_ratio_min = float(clip_log_ratio_min or 0.0)
+    a.clip_log_ratio_max = float(clip_log_ratio_max or 0.0)
+    a.value_clip = float(value_clip or 0.0)
+    a.huber_delta = float(huber_delta or 0.0)
+    a.max_episode_steps = int(max_episode_steps) if max_episode_steps else 0
+    a.critic_warmup = int(bool(critic_warmup))
+    a.entropy_bonus = float(entropy_bonus)
+    a.loss_scale = float(loss_scale)
+    ws = torch.empty(32, dtype=torch.float64, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    metrics = torch.empty(L.NUM_METRICS, dtype=torch.float32, device=dev)
+    d_lp = torch.empty_like(lp) if want_grads else None
+    d_v = torch.empty((values.numel(),), dtype=torch.float32, device=dev).view(values.shape) if (want_grads and with_critic) else None
+    d_e = torch.empty_like(keep[0]) if (want_grads and entropy is not None) else None
+    a.workspace, a.loss, a.metrics = L.ptr(ws), L.ptr(loss), L.ptr(metrics)
+    a.d_logprobs, a.d_values, a.d_entropy = L.ptr(d_lp), L.ptr(d_v), L.ptr(d_e)
+    L.check(lib.rb200_ppo_loss(C.byref(a), L.stream_ptr()), "ppo_loss")
+    return loss, metrics, d_lp, d_v, d_e
+
+
+def scale_(x: torch.Tensor, s: float) -> torch.Tensor:
+    lib = L.load()
+    L.check(lib.rb200_scale(L.ptr(x), x.numel(), float(s), L.stream_ptr()), "scale")
+    return x
+
+
+def scale_by_(x: torch.Tensor, s_dev: torch.Tensor) -> torch.Tensor:
+    """x *= s_dev[0] with the scalar read on the device (no host sync)."""
+    lib = L.load()
+    s = s_dev.reshape(1).to(torch.float32)
+    L.check(lib.rb200_scale_by(L.ptr(x), x.numel(), L.ptr(s), L.stream_ptr()), "scale_by")
+    return x
