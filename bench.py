@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/sec (rollout + PPO update) on the synthetic workload.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (default N=1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+One "step" = one runner iteration: T-step rollout of B envs on the device + advantages + the full PPO
+update (update_epoch x mini-batches, fused loss, backward, clip+AdamW) = B*T env-steps.
+Workload = BASELINE.json configs[1]: synthetic vector env obs_dim=128 act_dim=8, MLP policy, PPO,
+B=4096 T=512; hyper-parameters of examples/embodiment/config/maniskill_ppo_mlp.yaml.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (rollout+update)"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--T", type=int, default=512)
+    ap.add_argument("--obs", type=int, default=128)
+    ap.add_argument("--act", type=int, default=8)
+    ap.add_argument("--update-epoch", type=int, default=8)
+    ap.add_argument("--minibatches", type=int, default=8)
+    ap.add_argument("--cpu-envs", type=int, default=512, help="envs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-bench", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic vector env obs_dim={a.obs} act_dim={a.act}, MLP policy, PPO, B={a.B} T={a.T} "
+            f"(BASELINE configs[1]), update_epoch={a.update_epoch}, {a.minibatches} mini-batches/epoch")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.rows), "power_w_max": max(float(r[3]) for r in self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path, on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_iteration_rate(a, n_envs, steps, warmup):
+    import torch
+
+    from oracle.runner_oracle import RunnerOracle
+    from rlinf_b200.config import synthetic_ppo_config
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synthetic_ppo_config(B=n_envs, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
+                               num_minibatches=a.minibatches)
+    r = RunnerOracle(cfg)
+    times, timers = [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        r.run_iteration()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            timers.append(dict(r.timers))
+    mean = sum(times) / len(times)
+    phases = {k: sum(t[k] for t in timers) / len(timers) for k in timers[0]}
+    return n_envs * a.T / mean, mean, cores, phases
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_envs = min(a.cpu_envs, a.B)
+    value, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, a.steps, a.warmup)
+    sample = (f"{n_envs} of {a.B} envs x T={a.T} per step (same update_epoch/mini-batch structure); "
+              f"oracle port of the reference CPU path (torch {cores} threads); the reference's own Ray runner "
+              f"cannot be launched offline")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "B": a.B, "T": a.T, "obs_dim": a.obs, "act_dim": a.act},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "phases_s": phases},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def kernel_rooflines(a, peaks, torch):
+    """Live CUDA-event timing of the HBM-bound kernels at the workload's shapes. Each kernel is launched
+    from a captured CUDA graph over ROT independent input sets whose total size exceeds L2 (126 MB), so
+    every launch streams from HBM; per-launch time = graph time / launches (includes inter-kernel gaps)."""
+    from rlinf_b200 import ops
+
+    dev = torch.device("cuda")
+    T, B, A = a.T, a.B // max(a.gpus, 1), a.act
+    out = {}
+
+    def time_graph(fn, n_launch, reps=5):
+        fn()  # warm (allocations, descriptor encode)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = []
+        for _ in range(reps):
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best.append(e0.elapsed_time(e1) * 1e-3 / n_launch)
+        best.sort()
+        return best[len(best) // 2]
+
+    # ---- GAE scan: 17 B/step + bootstrap row ----
+    bytes_gae = 17 * T * B + 5 * B
+    rot = max(2, int(300e6 // bytes_gae) + 1)
+    sets = []
+    for i in range(rot):
+        r = torch.randn(T, B, device=dev)
+        v = torch.randn(T + 1, B, device=dev)
+        d = (torch.rand(T + 1, B, device=dev) < 0.01).view(torch.uint8)
+        sets.append((r, v, d, torch.empty(T, B, device=dev), torch.empty(T, B, device=dev),
+                     torch.empty(6, dtype=torch.float64, device=dev)))
+    from rlinf_b200 import _lib as L
+    lib = L.load()
+
+    def gae_all():
+        for (r, v, d, ad, rt, stt) in sets:
+            L.check(lib.rb200_gae(L.ptr(r), L.ptr(v), L.ptr(d), None, L.ptr(ad), L.ptr(rt), L.ptr(stt), T, B, 0.99,
+                                  0.95, L.stream_ptr()), "gae")
+
+    t = time_graph(gae_all, rot)
+    out["gae_scan"] = {"bound": "hbm", "achieved": bytes_gae / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": bytes_gae / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": t * 1e6,
+                       "algorithmic_bytes": bytes_gae, "launch_note": "includes the 48-byte stats memset node"}
+    del sets
+
+    # ---- fused gather + PPO loss fwd+bwd on one mini-batch: 124 B/sample ----
+    n_all = T * B
+    mb = n_all // a.minibatches
+    bytes_ppo = (8 + 4 * A + 4 * A + 16 + 4 * A + 4) * mb
+    old = torch.randn(n_all, A, device=dev) * 0.3 - 1
+    adv, ret, pv = (torch.randn(n_all, 1, device=dev) for _ in range(3))
+    perm = torch.randperm(n_all, device=dev)
+    rot = max(2, int(300e6 // bytes_ppo) + 1)
+    cur = [(torch.randn(mb, A, device=dev) * 0.3 - 1, torch.randn(mb, 1, device=dev)) for _ in range(rot)]
+    idxs = [perm[(i * mb) % n_all:][:mb].contiguous() for i in range(rot)]
+
+    def ppo_all():
+        for (lp, vv), ix in zip(cur, idxs):
+            ops.ppo_loss(logprobs=lp, values=vv, old_logprobs=old, advantages=adv, returns=ret, prev_values=pv,
+                         idx=ix, C_chunks=1, A_dim=A, logprob_type="action_level", value_clip=1.0, huber_delta=10.0)
+
+    t = time_graph(ppo_all, rot)
+    out["gather_ppo_loss_fwd_bwd"] = {"bound": "hbm", "achieved": bytes_ppo / t / 1e9, "peak": peaks["hbm_gbs"],
+                                      "unit": "GB/s", "frac": bytes_ppo / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                      "us_per_launch": t * 1e6, "algorithmic_bytes": bytes_ppo,
+                                      "launch_note": "memset + main + finalise nodes; rollout rows gathered through idx"}
+    return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rlinf_b200 import _lib as L
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    lib = L.load()
+    peaks = measured_peaks()
+    cfg = synthetic_ppo_config(B=a.B, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
+                               num_minibatches=a.minibatches)
+    run = EmbodiedRunner(cfg)
+    n_env_steps = a.B * a.T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # graph capture of the rollout happens on the 2nd call: make sure warm-up covers it
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        run.run_iteration()
+    barrier()
+
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps + 1)]
+    launches0 = lib.rb200_launch_count()
+    graph_nodes = run.rollout.graph_kernel_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    metrics = None
+    for i in range(a.steps):
+        run.update_rollout_weights()
+        run.rollout_phase()
+        ev[3 * i + 1].record()
+        metrics = run.update_phase()
+        ev[3 * i + 3].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    total_ms = ev[0].elapsed_time(ev[3 * a.steps])
+    rollout_ms = sum((ev[3 * i].elapsed_time(ev[3 * i + 1])) for i in range(a.steps)) / a.steps
+    launches = lib.rb200_launch_count() - launches0 + graph_nodes * a.steps
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    value = n_env_steps / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (the reference hands the actor CPU tensors) ----
+    def pin(d):
+        return {k: (pin(v) if isinstance(v, dict) else torch.empty(v.shape, dtype=v.dtype).pin_memory())
+                for k, v in d.items()}
+
+    host = pin(run.buffer.as_batch())
+
+    def nbytes(d):
+        return sum(nbytes(v) if isinstance(v, dict) else v.numel() * v.element_size() for v in d.values())
+
+    def d2h(src, dst):
+        for k, v in src.items():
+            if isinstance(v, dict):
+                d2h(v, dst[k])
+            else:
+                dst[k].copy_(v, non_blocking=True)
+
+    bytes_batch = nbytes(host)
+    for _ in range(1):
+        run.rollout_phase()
+        d2h(run.buffer.as_batch(), host)
+        torch.cuda.synchronize()
+        run.update_phase(batch=host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_steps = max(1, min(a.steps, 3))
+    for _ in range(e2e_steps):
+        run.update_rollout_weights()
+        run.rollout_phase()
+        d2h(run.buffer.as_batch(), host)           # rollout side -> host (what the reference's workers exchange)
+        torch.cuda.synchronize()
+        m = run.update_phase(batch=host)            # actor: H2D of the batch, advantages, update, metrics D2H
+    e1.record()
+    barrier()
+    e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_env_steps * e2e_steps / float(t.item())
+    metrics_bytes = 8 * 32
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "B": a.B, "T": a.T, "obs_dim": a.obs, "act_dim": a.act,
+                   "global_batch_size": cfg.actor.global_batch_size, "micro_batch_size": cfg.actor.micro_batch_size,
+                   "parallelism": f"dp{a.gpus} over envs, 1 NCCL all-reduce of the flat grad buffer / optimiser step",
+                   "l2": "per-step inputs (1.2 GB rollout batch / rank share) exceed the 126 MB L2; kernel "
+                         "micro-timings rotate >300 MB of inputs"},
+        "phases_ms": {"rollout": rollout_ms, "update": ms_per_step - rollout_ms},
+        "wall_ms_per_step": t_wall / a.steps * 1e3,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_batch,
+                "d2h_bytes_per_step": bytes_batch + metrics_bytes,
+                "note": "rollout batch staged through pinned host memory both ways, as between the reference's "
+                        "rollout/env workers and its actor"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "train_metrics": {k: v for k, v in (metrics or {}).items()},
+    }
+    if rank == 0:
+        # dominant kernel by time: the fp32 MLP GEMMs (forward, dgrad, wgrad) - flops known analytically
+        n = a.B * a.T // world
+        H, O, A = 256, a.obs, a.act
+        fwd = 2 * (O * H + 2 * H * H) * 2          # two towers
+        bwd = 2 * (O * H + 2 * H * H) * 2 + 2 * (2 * H * H) * 2  # wgrad (3 layers) + dgrad (2 layers), two towers
+        flops_update = (fwd + bwd) * n * a.update_epoch
+        upd_s = (ms_per_step - rollout_ms) * 1e-3
+        line["roofline"] = {
+            "kernel": "sgemm_kernel (MLP forward/dgrad/wgrad, fp32 SIMT in this round)", "bound": "tensor",
+            "achieved": flops_update / upd_s / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": flops_update / upd_s / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+            "note": f"dense-GEMM flops of the update phase / update time; peak = {peaks['source']} bf16 sustained; "
+                    "fp32 accumulate-exact path, tcgen05 3xTF32 path is the next step"}
+        if not a.no_kernel_bench:
+            try:
+                line["roofline_hbm_kernels"] = kernel_rooflines(a, peaks, torch)
+            except Exception as e:  # pragma: no cover
+                line["roofline_hbm_kernels"] = {"error": repr(e)}
+        if not a.no_cpu_baseline and world == 1:
+            n_envs = min(a.cpu_envs, a.B)
+            v, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, 1, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 iteration of {n_envs} of {a.B} envs x T={a.T}, same update structure; "
+                                              f"oracle port of the reference CPU path, torch {cores} threads",
+                                    "seconds": mean_s, "phases_s": phases}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,9 @@ int rb200_abi_version(void);
 const char* rb200_strerror(int code);
 /* sm count / compute capability of the current device (host-side query). */
 int rb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* kernels launched by this library in this process so far (host counter; launches replayed from a
+ * captured CUDA graph are counted once, at capture). */
+uint64_t rb200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * K0  loss mask            replaces compute_loss_mask, rlinf/utils/metric_utils.py:516-537
@@ -236,11 +239,39 @@ int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const flo
                        const float* acts, float* work, float* grads, rb200_stream_t stream);
 
 /* Rollout step (inference): mean/value forward, action = mean + exp(logstd)*noise where noise is
- * either supplied ([n,act], parity mode) or drawn from Philox(seed, offset) (noise == NULL);
+ * either supplied ([n,act], parity mode) or drawn from Philox(seed, offset + *counter_dev) (noise == NULL; counter_dev may be NULL);
  * writes action [n,act], logprobs [n,act], values [n,value_dim]. */
 int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* states,
-                     const float* noise, uint64_t seed, uint64_t offset, int64_t n, float* action,
-                     float* logprobs, float* values, float* work, rb200_stream_t stream);
+                     const float* noise, uint64_t seed, uint64_t offset, const uint64_t* counter_dev,
+                     int64_t n, float* action, float* logprobs, float* values, float* work,
+                     rb200_stream_t stream);
+
+/* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
+ * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */
+int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* states, int64_t n,
+                    float* values, float* work, rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rollout-side helpers (device-resident rollout loop; replaces the per-chunk-step Channel hops with
+ * CPU staging of env_worker.py:1087-1202 / huggingface_worker.py:678-704).
+ * ---------------------------------------------------------------------------------------- */
+/* Synthetic vector env step implementing the chunk_step contract (C = 1):
+ *   s' = tanh(s.W_s + a.W_a + noise_std*eps), r = -|s'|^2/obs + reward_noise_std*eps_r,
+ *   term ~ Bernoulli(p_term), trunc at max_episode_steps, auto-reset to N(0,I).
+ * w_s [obs,obs] (in,out), w_a [act,obs]; noise: optional pre-drawn [B, 2*obs+2] (parity mode), else
+ * Philox(seed, *counter_dev). final_obs = observation before the reset. */
+int rb200_synth_env_step(const float* w_s, const float* w_a, const float* state, const float* action,
+                         const float* noise, float* next_state, float* final_obs, float* reward,
+                         uint8_t* term, uint8_t* trunc, uint8_t* done, int32_t* elapsed, float* z_scratch,
+                         int B, int obs, int act, int max_episode_steps, int auto_reset, float p_term,
+                         float noise_std, float reward_noise_std, uint64_t seed,
+                         const uint64_t* counter_dev, rb200_stream_t stream);
+/* rewards[b] += gamma * final_values[b*value_dim] where flag[b]  (compute_bootstrap_rewards,
+ * workers/env/env_worker.py:736-758; flag = truncations ("standard") or dones ("always")). */
+int rb200_bootstrap_rewards(float* rewards, const float* final_values, const uint8_t* flag, int B,
+                            int value_dim, double gamma, rb200_stream_t stream);
+/* counter_dev[0] += inc (device-side RNG step counter so captured CUDA graphs replay fresh noise). */
+int rb200_counter_add(uint64_t* counter_dev, uint64_t inc, rb200_stream_t stream);
 
 #ifdef __cplusplus
 }

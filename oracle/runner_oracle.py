@@ -1,0 +1,211 @@
+"""CPU restatement of one EmbodiedRunner iteration (rollout + advantages + PPO update), single process.
+
+TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/rl_oracle.py header).  It is the `cpu_baseline` and the
+`--impl reference` arm of bench.py: the reference's own runner cannot be launched here (needs Ray, Hydra,
+OmegaConf and a simulator - SURVEY.md §8c), so this is the loop of rlinf/runners/embodied_runner.py:478-563
+restated with the worker-level steps in the reference's order and with the reference's data movement
+kept where it is cheap to keep (per-step `.cpu().contiguous()` staging is a no-op on CPU tensors; list
+appends + torch.stack are kept).  The Ray/Channel hops are omitted, which FAVOURS the baseline.
+
+Steps follow: env_worker.py:1059-1349 (_run_interact_once), huggingface_worker.py:678-781
+(generate_one_epoch), embodied_fsdp_actor_worker.py:187-321 (recv / advantages), :484-699 (run_training /
+train_micro_batch), fsdp_model_manager.py:429-463 (optimizer_step).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+
+from . import rl_oracle as O
+
+
+class SyntheticEnvCPU:
+    """Same dynamics as rlinf_b200.envs.SyntheticVectorEnv (same W_s/W_a from the same seed); own RNG."""
+
+    def __init__(self, num_envs, obs_dim, action_dim, max_episode_steps, auto_reset=True, p_term=0.005,
+                 noise_std=0.1, reward_noise_std=0.01, seed=1234):
+        g = torch.Generator().manual_seed(seed)
+        self.w_s = torch.randn(obs_dim, obs_dim, generator=g) / math.sqrt(obs_dim)
+        self.w_a = torch.randn(action_dim, obs_dim, generator=g) / math.sqrt(action_dim)
+        self.B, self.obs_dim = num_envs, obs_dim
+        self.max_episode_steps, self.auto_reset = max_episode_steps, auto_reset
+        self.p_term, self.noise_std, self.reward_noise_std = p_term, noise_std, reward_noise_std
+        self.gen = torch.Generator().manual_seed(seed + 1)
+        self.state = torch.zeros(num_envs, obs_dim)
+        self.elapsed = torch.zeros(num_envs, dtype=torch.int32)
+
+    def reset(self):
+        self.state = torch.randn(self.B, self.obs_dim, generator=self.gen)
+        self.elapsed.zero_()
+        return {"states": self.state}, {}
+
+    def step_given_noise(self, state, action, noise):
+        """Deterministic step with pre-drawn noise [B, 2*obs+2] (layout of rb200_synth_env_step)."""
+        obs = self.obs_dim
+        z = state @ self.w_s + action @ self.w_a
+        s = torch.tanh(z + self.noise_std * noise[:, :obs])
+        reward = -(s * s).sum(-1) / obs + self.reward_noise_std * noise[:, obs]
+        self.elapsed += 1
+        term = noise[:, obs + 1] < self.p_term
+        trunc = (self.elapsed >= self.max_episode_steps) if self.max_episode_steps > 0 else torch.zeros_like(term)
+        done = term | trunc
+        final = s
+        nxt = s
+        if self.auto_reset:
+            nxt = torch.where(done.unsqueeze(-1), noise[:, obs + 2:], s)
+            self.elapsed[done] = 0
+        return nxt, final, reward, term, trunc, done
+
+    def chunk_step(self, chunk_actions, noise=None):
+        B = self.B
+        if noise is None:
+            noise = torch.cat([torch.randn(B, self.obs_dim + 1, generator=self.gen),
+                               torch.rand(B, 1, generator=self.gen),
+                               torch.randn(B, self.obs_dim, generator=self.gen)], dim=1)
+        nxt, final, reward, term, trunc, done = self.step_given_noise(self.state, chunk_actions.reshape(B, -1), noise)
+        self.state = nxt
+        return ([{"states": nxt}], reward.view(B, 1), term.view(B, 1), trunc.view(B, 1),
+                [{"final_observation": {"states": final}}])
+
+
+class RunnerOracle:
+    def __init__(self, cfg, params=None):
+        self.cfg = cfg
+        m, et = cfg["actor"]["model"], cfg["env"]["train"]
+        self.B, self.T = et["total_num_envs"], et["max_steps_per_rollout_epoch"]
+        self.obs_dim, self.act_dim = m["obs_dim"], m["action_dim"] * m.get("num_action_chunks", 1)
+        self.params = params or O.mlp_init(self.obs_dim, m["action_dim"], m.get("num_action_chunks", 1),
+                                           seed=cfg["actor"]["seed"])
+        for p in self.params.values():
+            p.requires_grad_(True)
+        o = cfg["actor"]["optim"]
+        self.opt = O.build_adamw(self.params, o["lr"], o.get("value_lr", o["lr"]),
+                                 (o.get("adam_beta1", 0.9), o.get("adam_beta2", 0.999)), o.get("adam_eps", 1e-8),
+                                 o.get("weight_decay", 1e-2))
+        self.env = SyntheticEnvCPU(self.B, self.obs_dim, self.act_dim, et["max_episode_steps"], et["auto_reset"],
+                                   et.get("p_term", 0.005), et.get("noise_std", 0.1),
+                                   et.get("reward_noise_std", 0.01), et.get("seed", 1234))
+        self.gen = torch.Generator().manual_seed(cfg["actor"]["seed"])
+        self.obs = None
+        self.timers = {}
+
+    # -- rollout (env_worker.py:1059-1349 / huggingface_worker.py:678-781) -----------------------------
+    @torch.no_grad()
+    def rollout(self, policy_noise=None, env_noise=None):
+        """policy_noise [T+1,B,act] / env_noise [T,B,2*obs+2]: pre-drawn draws for parity tests."""
+        a = self.cfg["algorithm"]
+        gamma, boot_always = a.get("gamma", 1), a.get("bootstrap_type", "standard") != "standard"
+        B, T = self.B, self.T
+        if self.obs is None:
+            self.obs, _ = self.env.reset()
+        lists = {k: [] for k in ("rewards", "dones", "terminations", "truncations", "prev_values", "prev_logprobs",
+                                 "states", "action")}
+        dones = torch.zeros(B, 1, dtype=torch.bool)
+        term, trunc = dones.clone(), dones.clone()
+        rewards, final_obs = None, None
+        for t in range(T + 1):
+            states = self.obs["states"]
+            noise = policy_noise[t] if policy_noise is not None else torch.randn(B, self.act_dim, generator=self.gen)
+            action, logp, values = O.mlp_sample(self.params, states, noise)
+            boot = None
+            if final_obs is not None:  # get_bootstrap_values: second forward on final_obs
+                boot = O.mlp_forward(self.params, final_obs["states"], None, want_entropy=False)["values"][:, :1]
+            if rewards is not None:  # compute_bootstrap_rewards
+                adj = rewards.clone()
+                flag = (dones if boot_always else trunc)[:, -1]
+                if boot is not None and self.env.auto_reset and bool(flag.any()):
+                    fv = torch.zeros_like(adj[:, -1])
+                    fv[flag] = boot[flag].reshape(-1)
+                    adj[:, -1] += gamma * fv
+                lists["rewards"].append(adj.contiguous())
+            lists["dones"].append(dones.contiguous())
+            lists["terminations"].append(term.contiguous())
+            lists["truncations"].append(trunc.contiguous())
+            lists["prev_values"].append(values.contiguous())
+            if t == T:
+                break
+            lists["prev_logprobs"].append(logp.contiguous())
+            lists["states"].append(states.contiguous())
+            lists["action"].append(action.contiguous())
+            obs_list, rewards, term, trunc, infos = self.env.chunk_step(
+                action.reshape(B, 1, -1), None if env_noise is None else env_noise[t])
+            self.obs = obs_list[-1]
+            dones = term | trunc
+            final_obs = infos[-1]["final_observation"]
+        batch = {k: torch.stack(v, dim=0) for k, v in lists.items() if k not in ("states", "action")}
+        batch["forward_inputs"] = {"states": torch.stack(lists["states"], 0), "action": torch.stack(lists["action"], 0)}
+        return batch
+
+    # -- advantages + update ---------------------------------------------------------------------------
+    def update(self, batch, rank=0, world_size=1):
+        cfg, a = self.cfg, self.cfg["algorithm"]
+        t0 = time.perf_counter()
+        if not cfg["env"]["train"]["auto_reset"] and not cfg["env"]["train"].get("ignore_terminations", False):
+            batch["loss_mask"], batch["loss_mask_sum"] = O.loss_mask_from_dones(batch["dones"])
+        res = O.adv_and_returns_embodied(a["adv_type"], batch["rewards"], batch["dones"], batch.get("prev_values"),
+                                         batch.get("loss_mask"), batch.get("loss_mask_sum"), a.get("gamma", 1),
+                                         a.get("gae_lambda", 1), a.get("group_size", 8), a["reward_type"])
+        batch.update(res)
+        t1 = time.perf_counter()
+        n = batch["prev_logprobs"].shape[0] * batch["prev_logprobs"].shape[1]
+        perm = O.shuffle_indices(n, cfg["actor"]["seed"] + rank)
+        with torch.no_grad():
+            flat = O.flatten_and_shuffle(batch, perm)
+        per_rank = cfg["actor"]["global_batch_size"] // world_size
+        mbs = cfg["actor"]["micro_batch_size"]
+        accum = per_rank // mbs
+        with_critic = a["adv_type"] == "gae"
+        A = cfg["actor"]["model"]["action_dim"]
+        ent_bonus = a.get("entropy_bonus", 0) or 0
+        metrics = {}
+        for _ in range(a.get("update_epoch", 1)):
+            for gb in range(n // per_rank):
+                self.opt.zero_grad()
+                for k in range(accum):
+                    lo = gb * per_rank + k * mbs
+                    sl = slice(lo, lo + mbs)
+                    out = O.mlp_forward(self.params, flat["forward_inputs"]["states"][sl],
+                                        flat["forward_inputs"]["action"][sl], want_entropy=ent_bonus > 0,
+                                        want_values=with_critic)
+                    loss, md = O.policy_loss_embodied(
+                        a["loss_type"], out["logprobs"], flat["prev_logprobs"][sl], flat["advantages"][sl],
+                        a["logprob_type"], A, loss_mask=None if flat.get("loss_mask") is None else flat["loss_mask"][sl],
+                        loss_mask_sum=None if flat.get("loss_mask_sum") is None else flat["loss_mask_sum"][sl],
+                        values=out.get("values") if with_critic else None,
+                        prev_values=flat["prev_values"][sl] if with_critic else None,
+                        returns=flat["returns"][sl] if with_critic else None, reward_type=a["reward_type"],
+                        clip_ratio_low=a["clip_ratio_low"], clip_ratio_high=a["clip_ratio_high"],
+                        value_clip=a.get("value_clip"), huber_delta=a.get("huber_delta"),
+                        max_episode_steps=cfg["env"]["train"]["max_episode_steps"] if flat.get("loss_mask_sum") is not None else None)
+                    if ent_bonus > 0:
+                        ent = O.entropy_term(out["entropy"], a["entropy_type"], A, out["logprobs"].shape[0],
+                                             None if flat.get("loss_mask") is None else flat["loss_mask"][sl])
+                        loss = loss - ent_bonus * ent
+                        md["actor/entropy_loss"] = float(ent.detach())
+                    loss = loss / accum
+                    loss.backward()
+                    md["actor/total_loss"] = float(loss.detach())
+                    for kk, vv in md.items():
+                        metrics.setdefault(kk, []).append(vv)
+                gn = O.optimizer_step(self.opt, self.params, cfg["actor"]["optim"]["clip_grad"])
+                metrics.setdefault("actor/grad_norm", []).append(gn)
+        t2 = time.perf_counter()
+        self.timers = {"adv_s": t1 - t0, "train_s": t2 - t1}
+        ev = {k: sum(v) for k, v in metrics.items() if k.startswith(O.EV_PREFIX)}
+        out = {k: sum(v) / len(v) for k, v in metrics.items() if not k.startswith(O.EV_PREFIX)}
+        if ev:
+            cnt = ev[O.EV_PREFIX + "count"]
+            rc = ev[O.EV_PREFIX + "returns_sq_sum"] - ev[O.EV_PREFIX + "returns_sum"] ** 2 / max(cnt, 1)
+            ec = ev[O.EV_PREFIX + "errors_sq_sum"] - ev[O.EV_PREFIX + "errors_sum"] ** 2 / max(cnt, 1)
+            out["critic/explained_variance"] = (1 - ec / rc) if (cnt >= 2 and rc != 0) else float("nan")
+        return out
+
+    def run_iteration(self):
+        t0 = time.perf_counter()
+        batch = self.rollout()
+        t1 = time.perf_counter()
+        m = self.update(batch)
+        self.timers["rollout_s"] = t1 - t0
+        return m

@@ -71,6 +71,7 @@ SIGNATURES = {
     "rb200_abi_version": (c_int, []),
     "rb200_strerror": (C.c_char_p, [c_int]),
     "rb200_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "rb200_launch_count": (c_uint64, []),
     "rb200_loss_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rb200_gae": (c_int, [c_void_p] * 7 + [c_int, c_int, c_double, c_double, c_void_p]),
     "rb200_normalize": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
@@ -88,7 +89,11 @@ SIGNATURES = {
     "rb200_mlp_fwd_scratch_floats": (c_int64, [C.POINTER(MlpLayout), c_int64]),
     "rb200_mlp_forward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 4 + [c_int64] + [c_void_p] * 5),
     "rb200_mlp_backward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 4 + [c_int64] + [c_void_p] * 7),
-    "rb200_mlp_sample": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 3 + [c_uint64, c_uint64, c_int64] + [c_void_p] * 5),
+    "rb200_mlp_sample": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 3 + [c_uint64, c_uint64, c_void_p, c_int64] + [c_void_p] * 5),
+    "rb200_mlp_value": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "rb200_synth_env_step": (c_int, [c_void_p] * 13 + [c_int] * 5 + [c_float] * 3 + [c_uint64, c_void_p, c_void_p]),
+    "rb200_bootstrap_rewards": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),
+    "rb200_counter_add": (c_int, [c_void_p, c_uint64, c_void_p]),
 }
 
 _LIB: Optional[C.CDLL] = None

@@ -43,7 +43,7 @@ def _digest() -> str:
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
         os.path.join(os.path.dirname(PKG_DIR), "include", "rlinf_b200.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 namespace rb {
+static unsigned long long g_launches = 0;
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+unsigned long long launches() { return g_launches; }
 double* device_scratch(int n_doubles_min) {
   static double* ptr[64] = {nullptr};
   static int cap[64] = {0};
@@ -20,6 +23,9 @@ double* device_scratch(int n_doubles_min) {
   return ptr[dev];
 }
 }  // namespace rb
+
+namespace rb { unsigned long long launches(); }
+extern "C" uint64_t rb200_launch_count(void) { return rb::launches(); }
 
 extern "C" int rb200_abi_version(void) { return RB200_ABI_VERSION; }
 

@@ -113,7 +113,7 @@ extern "C" int rb200_grad_sqnorm(const float* grads, int64_t n, double* out_sq, 
   const int64_t cap = (int64_t)rb::sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sqnorm_kernel<<<(int)blocks, 256, 0, st>>>(grads, n, out_sq);
+  sqnorm_kernel<<<(int)blocks, 256, 0, st>>>(grads, n, out_sq); rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
@@ -140,11 +140,11 @@ extern "C" int rb200_adamw_step(float* params, const float* grads, float* exp_av
   }
   if (grp.end[n_groups - 1] != n) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  adamw_prepare_kernel<<<1, 32, 0, st>>>(grad_sq, state, max_grad_norm, grad_scale);
+  adamw_prepare_kernel<<<1, 32, 0, st>>>(grad_sq, state, max_grad_norm, grad_scale); rb::count_launch();
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 4;
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grp, beta1, beta2, eps,
-                                            weight_decay, grad_scale, state);
+                                            weight_decay, grad_scale, state); rb::count_launch();
   RB_RETURN_LAUNCH();
 }

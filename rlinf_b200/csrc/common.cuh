@@ -51,6 +51,9 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* smem /* K*32 d
   }
 }
 
+// number of kernels this library has launched (host-side counter; bench.py's gpu_launches)
+void count_launch(int n = 1);
+
 inline cudaStream_t as_stream(rb200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Per-device scratch (reduction slots); allocated on first use, never freed.

@@ -262,13 +262,13 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
     if (!HAS_MASK) tm_m = tm_d;
     if (!e) {
       gae_tma_kernel<HAS_V, HAS_MASK, HAS_STATS>
-          <<<grid, 64, 0, st>>>(tm_r, tm_v, tm_d, tm_m, values, adv, ret, stats, T, B, gamma, coef);
+          <<<grid, 64, 0, st>>>(tm_r, tm_v, tm_d, tm_m, values, adv, ret, stats, T, B, gamma, coef); rb::count_launch();
       RB_RETURN_LAUNCH();
     }
     // descriptor encode failed (e.g. driver entry point unavailable): use the generic kernel
   }
   gae_generic_kernel<HAS_V, HAS_MASK, HAS_STATS>
-      <<<grid, 32, 0, st>>>(rewards, values, dones, mask, adv, ret, stats, T, B, gamma, coef);
+      <<<grid, 32, 0, st>>>(rewards, values, dones, mask, adv, ret, stats, T, B, gamma, coef); rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
@@ -312,6 +312,6 @@ extern "C" int rb200_normalize(float* x, const double* stats, int64_t n_elems, f
   const int64_t cap = (int64_t)rb::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  normalize_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, stats, n_elems, eps);
+  normalize_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, stats, n_elems, eps); rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -53,14 +53,14 @@ extern "C" int rb200_gather_rows(const void* src, const int64_t* idx, void* dst,
     const int vpr = (int)(row_bytes / 16);
     gather_rows_vec16<<<grid_for(n_rows_out * vpr), 256, 0, st>>>(static_cast<const uint4*>(src), idx,
                                                                    static_cast<uint4*>(dst), n_rows_out, n_rows_src,
-                                                                   vpr);
+                                                                   vpr); rb::count_launch();
   } else if (row_bytes % 4 == 0 && (a & 3) == 0) {
     const int epr = (int)(row_bytes / 4);
     gather_rows_small<uint32_t><<<grid_for(n_rows_out * epr), 256, 0, st>>>(
-        static_cast<const uint32_t*>(src), idx, static_cast<uint32_t*>(dst), n_rows_out, n_rows_src, epr);
+        static_cast<const uint32_t*>(src), idx, static_cast<uint32_t*>(dst), n_rows_out, n_rows_src, epr); rb::count_launch();
   } else {
     gather_rows_small<uint8_t><<<grid_for(n_rows_out * row_bytes), 256, 0, st>>>(
-        static_cast<const uint8_t*>(src), idx, static_cast<uint8_t*>(dst), n_rows_out, n_rows_src, (int)row_bytes);
+        static_cast<const uint8_t*>(src), idx, static_cast<uint8_t*>(dst), n_rows_out, n_rows_src, (int)row_bytes); rb::count_launch();
   }
   RB_RETURN_LAUNCH();
 }

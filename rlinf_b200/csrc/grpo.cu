@@ -76,7 +76,7 @@ extern "C" int rb200_grpo_scores(const float* rewards, const uint8_t* dones, flo
                                  rb200_stream_t stream) {
   if (!rewards || !dones || !scores) return RB200_E_NULL;
   if (T <= 0 || B <= 0) return RB200_E_SHAPE;
-  grpo_scores_kernel<<<(B + 31) / 32, 32, 0, rb::as_stream(stream)>>>(rewards, dones, scores, T, B);
+  grpo_scores_kernel<<<(B + 31) / 32, 32, 0, rb::as_stream(stream)>>>(rewards, dones, scores, T, B); rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
@@ -85,6 +85,6 @@ extern "C" int rb200_grpo_advantages(const float* scores, const uint8_t* loss_ma
   if (!scores || !adv) return RB200_E_NULL;
   if (T <= 0 || B <= 0 || G <= 0 || B % G != 0) return RB200_E_SHAPE;
   grpo_adv_kernel<<<(B + kCols - 1) / kCols, kCols * kRowsPar, 0, rb::as_stream(stream)>>>(scores, loss_mask, adv, T,
-                                                                                           B, G, eps);
+                                                                                           B, G, eps); rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -55,6 +55,6 @@ extern "C" int rb200_loss_mask(const uint8_t* dones, uint8_t* mask, int64_t* mas
   if (!dones || !mask || !mask_sum) return RB200_E_NULL;
   if (nc <= 0 || B <= 0 || C <= 0) return RB200_E_SHAPE;
   const int grid = (B + kCols - 1) / kCols;
-  loss_mask_kernel<<<grid, kCols * kRowsPar, 0, rb::as_stream(stream)>>>(dones, mask, mask_sum, nc, B, C);
+  loss_mask_kernel<<<grid, kCols * kRowsPar, 0, rb::as_stream(stream)>>>(dones, mask, mask_sum, nc, B, C); rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -377,12 +377,16 @@ extern "C" int rb200_ppo_loss(const rb200_ppo_args* args, rb200_stream_t stream)
   int64_t blocks = (n_units + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  if (a.loss_mask) mask_count_kernel<<<(int)blocks, 256, 0, st>>>(a.loss_mask, a.idx, a.bsz, U, a.workspace);
+  if (a.loss_mask) {
+    mask_count_kernel<<<(int)blocks, 256, 0, st>>>(a.loss_mask, a.idx, a.bsz, U, a.workspace);
+    rb::count_launch();
+  }
   if (a.logprob_type == RB200_LOGPROB_TOKEN)
     ppo_main_kernel<true><<<(int)blocks, 256, 0, st>>>(a, h, U, g, a.workspace);
   else
     ppo_main_kernel<false><<<(int)blocks, 256, 0, st>>>(a, h, U, g, a.workspace);
-  ppo_finalize_kernel<<<1, 32, 0, st>>>(a, h, U, g, a.logprob_type == RB200_LOGPROB_TOKEN ? 1 : 0, a.workspace);
+  rb::count_launch();
+  ppo_finalize_kernel<<<1, 32, 0, st>>>(a, h, U, g, a.logprob_type == RB200_LOGPROB_TOKEN ? 1 : 0, a.workspace); rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
@@ -392,7 +396,7 @@ extern "C" int rb200_scale(float* x, int64_t n, float s, rb200_stream_t stream) 
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  scale_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, n, s);
+  scale_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, n, s); rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
@@ -402,6 +406,6 @@ extern "C" int rb200_scale_by(float* x, int64_t n, const float* s_dev, rb200_str
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  scale_by_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, n, s_dev);
+  scale_by_kernel<<<(int)blocks, 256, 0, rb::as_stream(stream)>>>(x, n, s_dev); rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -146,21 +146,34 @@ class MLPPolicy:
                                        L.ptr(acts), L.ptr(work), L.ptr(self.flat_grads), L.stream_ptr()),
                 "mlp_backward")
 
-    def sample(self, states, noise=None, seed=0, offset=0, calculate_values=True):
+    def sample(self, states, noise=None, seed=0, offset=0, calculate_values=True, counter=None, out=None):
         """_generate_actions(mode="train") (mlp_policy.py:256-293): action ~ N(mean, exp(logstd)),
         log_prob, value. `noise` ([n,act] N(0,1) draws) makes the step reproducible for parity tests;
         otherwise Philox(seed, offset) on the device."""
         lib = L.load()
         n = states.shape[0]
         work = self._buf("sample", 6 * n * HIDDEN + 64)
-        action = torch.empty((n, self.act_dim), dtype=torch.float32, device=self.device)
-        logp = torch.empty_like(action)
-        vals = torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device) if (
-            calculate_values and self.value_dim > 0) else None
+        if out is not None:  # write straight into rollout-buffer rows
+            action, logp, vals = out
+        else:
+            action = torch.empty((n, self.act_dim), dtype=torch.float32, device=self.device)
+            logp = torch.empty_like(action)
+            vals = torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device) if (
+                calculate_values and self.value_dim > 0) else None
         L.check(lib.rb200_mlp_sample(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), L.ptr(noise),
-                                     int(seed), int(offset), n, L.ptr(action), L.ptr(logp), L.ptr(vals), L.ptr(work),
-                                     L.stream_ptr()), "mlp_sample")
+                                     int(seed), int(offset), L.ptr(counter), n, L.ptr(action), L.ptr(logp),
+                                     L.ptr(vals), L.ptr(work), L.stream_ptr()), "mlp_sample")
         return action, logp, vals
+
+    def value(self, states, out=None):
+        """ValueHead(states) only - bootstrap values of final observations."""
+        lib = L.load()
+        n = states.shape[0]
+        work = self._buf("value", 3 * n * HIDDEN + 64)
+        vals = out if out is not None else torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device)
+        L.check(lib.rb200_mlp_value(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), n, L.ptr(vals),
+                                    L.ptr(work), L.stream_ptr()), "mlp_value")
+        return vals
 
     def predict_action_batch(self, env_obs, calculate_values=True, noise=None, seed=0, offset=0, **kwargs):
         """predict_action_batch (mlp_policy.py:296-321): returns (chunk_actions [B,C,A], result dict)."""

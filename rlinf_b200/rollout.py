@@ -1,0 +1,124 @@
+"""Device-resident rollout: buffer layout and the T-step env/policy loop.
+
+Replaces, for one rank, the ping-pong of EnvWorker._run_interact_once
+(rlinf/workers/env/env_worker.py:1059-1349) and MultiStepRolloutWorker.generate_one_epoch
+(rlinf/workers/rollout/hf/huggingface_worker.py:678-781): per chunk step the reference does two
+Channel hops with CPU staging and appends [B,...] CPU tensors to Python lists that are later
+`torch.stack`ed (rlinf/data/schema/embodied_trajectory_builder.py:72-231).  Here the trajectory rows
+are written by the kernels directly into one `[T(+1), B, ...]` buffer in HBM - the layout
+`convert_trajectories_to_batch` would produce (rlinf/data/schema/embodied_types.py:500):
+  rewards / actions / prev_logprobs / forward_inputs{states,action}: T rows,
+  dones / terminations / truncations / prev_values: T+1 rows (one bootstrap row)  [SURVEY A12].
+Row alignment (env_worker.py:1120-1202): row t holds the action/logprob/value computed from obs_t,
+`dones[t]` = done flags produced by step t-1 (row 0 all False), `rewards[t]` = reward of step t with the
+truncation bootstrap gamma*V(final_obs) already folded in.
+The whole loop is captured once in a CUDA graph (rollout.enable_cuda_graph) and replayed.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+class RolloutBuffer:
+    def __init__(self, T, B, obs_dim, act_dim, value_dim=1, device=None):
+        dev = device or L.default_device()
+        self.T, self.B, self.obs_dim, self.act_dim, self.value_dim = T, B, obs_dim, act_dim, value_dim
+        f32, u8 = torch.float32, torch.uint8
+        self.states = torch.zeros(T + 1, B, obs_dim, dtype=f32, device=dev)  # row T = bootstrap observation
+        self.actions = torch.zeros(T, B, act_dim, dtype=f32, device=dev)
+        self.prev_logprobs = torch.zeros(T, B, act_dim, dtype=f32, device=dev)
+        self.prev_values = torch.zeros(T + 1, B, value_dim, dtype=f32, device=dev)
+        self.rewards = torch.zeros(T, B, 1, dtype=f32, device=dev)
+        self.dones = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
+        self.terminations = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
+        self.truncations = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
+        self.final_obs = torch.zeros(B, obs_dim, dtype=f32, device=dev)
+        self.final_values = torch.zeros(B, value_dim, dtype=f32, device=dev)
+
+    def as_batch(self) -> dict:
+        """The rollout batch dict the actor consumes (keys of Trajectory / convert_trajectories_to_batch)."""
+        return {
+            "rewards": self.rewards,
+            "dones": self.dones.view(torch.bool),
+            "terminations": self.terminations.view(torch.bool),
+            "truncations": self.truncations.view(torch.bool),
+            "prev_values": self.prev_values,
+            "prev_logprobs": self.prev_logprobs,
+            "forward_inputs": {"states": self.states[: self.T], "action": self.actions},
+        }
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (
+            self.states[: self.T], self.actions, self.prev_logprobs, self.prev_values, self.rewards, self.dones,
+            self.terminations, self.truncations))
+
+
+class RolloutWorker:
+    """One rank's env + policy replica."""
+
+    def __init__(self, cfg, policy, env, buffer: RolloutBuffer):
+        self.cfg, self.policy, self.env, self.buf = cfg, policy, env, buffer
+        self.gamma = float(cfg.algorithm.get("gamma", 1))
+        self.bootstrap_type = cfg.algorithm.get("bootstrap_type", "standard")
+        self.auto_reset = bool(cfg.env.train.auto_reset)
+        self.seed = int(cfg.actor.seed)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=policy.device)
+        self._graph = None
+        self._use_graph = bool(cfg.rollout.get("enable_cuda_graph", True))
+        self.started = False
+        self._calls = 0
+        self.graph_kernel_count = 0  # kernels replayed per rollout once the CUDA graph exists
+
+    def _one_rollout(self, policy_noise=None, env_noise=None):
+        """policy_noise [T,B,act] / env_noise [T,B,2*obs+2]: pre-drawn N(0,1)/U(0,1) draws (parity tests);
+        None -> Philox on the device."""
+        lib = L.load()
+        buf, pol, env = self.buf, self.policy, self.env
+        T, B = buf.T, buf.B
+        st = L.stream_ptr()
+        for t in range(T):
+            # policy/value inference on obs_t -> action, logprob, value rows t  (predict_action_batch)
+            pol.sample(buf.states[t], noise=None if policy_noise is None else policy_noise[t], seed=self.seed,
+                       offset=0, counter=self.counter, out=(buf.actions[t], buf.prev_logprobs[t], buf.prev_values[t]))
+            L.check(lib.rb200_counter_add(L.ptr(self.counter), 1, st), "counter_add")
+            # env.chunk_step: writes obs_{t+1} (row t+1), reward t, flags row t+1
+            env.step_into(buf.states[t], buf.actions[t], buf.states[t + 1], buf.final_obs,
+                          buf.rewards[t].view(B), buf.terminations[t + 1].view(B), buf.truncations[t + 1].view(B),
+                          buf.dones[t + 1].view(B), noise=None if env_noise is None else env_noise[t])
+            # compute_bootstrap_rewards (env_worker.py:719-758): r += gamma * V(final_obs) where truncated/done
+            if self.auto_reset and pol.value_dim > 0:
+                pol.value(buf.final_obs, out=buf.final_values)
+                flag = buf.truncations[t + 1] if self.bootstrap_type == "standard" else buf.dones[t + 1]
+                L.check(lib.rb200_bootstrap_rewards(L.ptr(buf.rewards[t]), L.ptr(buf.final_values),
+                                                    L.ptr(flag.view(B)), B, pol.value_dim, self.gamma, st),
+                        "bootstrap_rewards")
+        # final extra inference for the bootstrap value row T (env_worker.py:1237-1306)
+        if pol.value_dim > 0:
+            pol.value(buf.states[T], out=buf.prev_values[T])
+
+    def generate(self):
+        """One rollout epoch of T steps into the buffer (all on the current stream, no host sync)."""
+        buf = self.buf
+        if not self.started:
+            obs, _ = self.env.reset()
+            buf.states[0].copy_(obs["states"])
+            self.started = True
+        else:
+            buf.states[0].copy_(buf.states[buf.T])  # last obs of the previous rollout (bootstrap_step)
+        # dones row 0 = zeros (env_worker.py:899-945): never written by the loop, stays zero
+        if not self._use_graph or self._calls == 0:
+            self._one_rollout()  # first call runs eagerly (also allocates every scratch buffer)
+            self._calls += 1
+            return
+        if self._graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.load().rb200_launch_count()
+            with torch.cuda.graph(g):
+                self._one_rollout()
+            self.graph_kernel_count = int(L.load().rb200_launch_count() - n0)
+            self._graph = g
+        self._graph.replay()
+        self._calls += 1

@@ -1,0 +1,136 @@
+"""GPU end-to-end parity: device rollout buffer alignment, synthetic env, and the PPO update
+(shuffle -> micro-batches -> fused loss -> backward -> clip+AdamW) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rl_oracle as O
+from oracle.runner_oracle import RunnerOracle, SyntheticEnvCPU
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_batch(b):
+    return {k: (_cpu_batch(v) if isinstance(v, dict) else v.detach().cpu().clone()) for k, v in b.items()}
+
+
+def test_env_step_given_noise_matches_cpu():
+    from rlinf_b200.envs import SyntheticVectorEnv
+
+    B, obs, act = 300, 24, 3
+    env = SyntheticVectorEnv(B, obs, act, max_episode_steps=5, p_term=0.2, seed=7)
+    ref = SyntheticEnvCPU(B, obs, act, max_episode_steps=5, p_term=0.2, seed=7)
+    assert torch.equal(env.w_s.cpu(), ref.w_s) and torch.equal(env.w_a.cpu(), ref.w_a)
+    g = torch.Generator().manual_seed(0)
+    state = torch.randn(B, obs, generator=g)
+    env.state.copy_(state)
+    ref.state = state.clone()
+    for step in range(12):
+        action = torch.randn(B, act, generator=g)
+        noise = torch.cat([torch.randn(B, obs + 1, generator=g), torch.rand(B, 1, generator=g),
+                           torch.randn(B, obs, generator=g)], 1)
+        obs_l, r, te, tr, infos = env.chunk_step(action.cuda().view(B, 1, act), noise=noise.cuda())
+        robs, rr, rte, rtr, rinf = ref.chunk_step(action.view(B, 1, act), noise)
+        assert torch.equal(te.cpu(), rte) and torch.equal(tr.cpu(), rtr), step
+        torch.testing.assert_close(r.cpu(), rr, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(obs_l[-1]["states"].cpu(), robs[-1]["states"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(infos[-1]["final_observation"]["states"].cpu(),
+                                   rinf[-1]["final_observation"]["states"], rtol=1e-4, atol=1e-6)
+        # keep the two copies in lock-step (tanh differs by ulps between libm and CUDA)
+        env.state.copy_(ref.state)
+    assert (ref.elapsed == env.elapsed.cpu()).all()
+
+
+@pytest.mark.parametrize("bootstrap_type", ["always", "standard"])
+def test_rollout_buffer_alignment_vs_oracle(bootstrap_type):
+    """Rows of the on-device [T(+1),B,...] buffer equal what the reference's trajectory builder would
+    stack, for the same injected policy/env noise (incl. truncation bootstrap folded into rewards)."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    B, T, obs, act = 64, 24, 6, 2
+    cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, **{"algorithm.bootstrap_type": bootstrap_type,
+                                                                          "env.train.p_term": 0.05,
+                                                                          "rollout.enable_cuda_graph": False})
+    run = EmbodiedRunner(cfg)
+    orc = RunnerOracle(cfg, params={n: p.detach().cpu().clone() for n, p in run.actor.model.named_parameters()})
+    g = torch.Generator().manual_seed(3)
+    pn = torch.randn(T + 1, B, act, generator=g)
+    en = torch.cat([torch.randn(T, B, obs + 1, generator=g), torch.rand(T, B, 1, generator=g),
+                    torch.randn(T, B, obs, generator=g)], -1)
+    s0 = torch.randn(B, obs, generator=g)
+    orc.env.state = s0.clone()
+    orc.obs = {"states": orc.env.state}
+    ob = orc.rollout(policy_noise=pn, env_noise=en)
+    run.rollout.started = True
+    run.buffer.states[0].copy_(s0)
+    run.rollout._one_rollout(policy_noise=pn.cuda(), env_noise=en.cuda())
+    b = _cpu_batch(run.buffer.as_batch())
+    for k in ("dones", "terminations", "truncations"):
+        assert torch.equal(b[k], ob[k]), k
+    assert bool(ob["dones"].any()) and ob["dones"].shape == (T + 1, B, 1) and ob["rewards"].shape == (T, B, 1)
+    for k in ("rewards", "prev_values", "prev_logprobs"):
+        torch.testing.assert_close(b[k], ob[k], rtol=1e-4, atol=2e-5, msg=k)
+    torch.testing.assert_close(b["forward_inputs"]["states"], ob["forward_inputs"]["states"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["forward_inputs"]["action"], ob["forward_inputs"]["action"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_update_matches_oracle_after_k_steps(accum):
+    """Same rollout batch -> advantages -> shuffled mini/micro-batches -> k optimiser steps: parameters,
+    metrics within 1e-4 rel (fp32) of the oracle."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    B, T, obs, act = 64, 32, 4, 2  # BASELINE config 1
+    n = B * T
+    cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, update_epoch=2, num_minibatches=4,
+                               micro_batch_size=n // 4 // accum)
+    run = EmbodiedRunner(cfg)
+    run.rollout_phase()
+    torch.cuda.synchronize()
+    batch = _cpu_batch(run.buffer.as_batch())
+    orc = RunnerOracle(cfg, params={k: p.detach().cpu().clone() for k, p in run.actor.model.named_parameters()})
+    om = orc.update(batch)
+    m = run.update_phase()
+    for name, p in run.actor.model.named_parameters():
+        torch.testing.assert_close(p.cpu(), orc.params[name].detach(), rtol=1e-4, atol=1e-6, msg=name)
+    for k, v in om.items():
+        if k in ("critic/value_clip_ratio",):
+            continue
+        assert k in m, k
+        np.testing.assert_allclose(m[k], v, rtol=2e-4, atol=1e-6, err_msg=k)
+    assert run.actor.optimizer.state[0].item() == 8
+
+
+def test_full_iterations_with_cuda_graph_rollout():
+    """3 iterations (eager rollout, graph capture, graph replay): finite metrics, fresh noise per replay,
+    value loss decreasing on the synthetic task."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    cfg = synthetic_ppo_config(B=256, T=16, obs_dim=8, action_dim=2, update_epoch=2, num_minibatches=2)
+    run = EmbodiedRunner(cfg)
+    ms, acts = [], []
+    for _ in range(3):
+        ms.append(run.run_iteration())
+        acts.append(run.buffer.actions.clone())
+    assert all(np.isfinite(v) for m in ms for k, v in m.items() if k != "critic/explained_variance")
+    assert not torch.equal(acts[1], acts[2])
+    assert run.rollout._graph is not None
+
+
+def test_host_batch_e2e_equals_device_batch():
+    """recv_rollout_trajectories accepts HOST tensors (as the reference's channel delivers them)."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    cfg = synthetic_ppo_config(B=64, T=16, obs_dim=4, action_dim=2, update_epoch=1, num_minibatches=2)
+    a, b = EmbodiedRunner(cfg), EmbodiedRunner(cfg)
+    a.rollout_phase()
+    torch.cuda.synchronize()
+    host = _cpu_batch(a.buffer.as_batch())
+    ma = a.update_phase()
+    mb = b.update_phase(batch=host)
+    assert torch.equal(a.actor.model.flat_params, b.actor.model.flat_params)
+    assert ma == mb
