@@ -28,6 +28,10 @@ METRIC = "env-steps/sec (rollout+update)"
 UNIT = "env-steps/s"
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,7 +44,8 @@ def parse():
     ap.add_argument("--act", type=int, default=8)
     ap.add_argument("--update-epoch", type=int, default=8)
     ap.add_argument("--minibatches", type=int, default=8)
-    ap.add_argument("--cpu-envs", type=int, default=512, help="envs in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-envs", type=int, default=0,
+                    help="envs in the bounded CPU sample (0 = 512 for cpu_baseline, 256 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-bench", action="store_true")
     return ap.parse_args()
@@ -69,10 +74,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
@@ -81,10 +86,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -101,13 +106,31 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path, on the host cores
 # ------------------------------------------------------------------------------------------------
+def effective_cores() -> int:
+    """Host cores this process may actually use: min(visible CPUs, affinity mask, cgroup CPU quota).
+    (The GPU boxes show 128 CPUs but cap the container at 16 via cpu.max; 128 threads on 16 cores is
+    ~50x slower than 16 threads.)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_iteration_rate(a, n_envs, steps, warmup):
     import torch
 
     from oracle.runner_oracle import RunnerOracle
     from rlinf_b200.config import synthetic_ppo_config
 
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     torch.set_num_threads(cores)
     cfg = synthetic_ppo_config(B=n_envs, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
                                num_minibatches=a.minibatches)
@@ -129,10 +152,10 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_envs = min(a.cpu_envs, a.B)
+    n_envs = min(a.cpu_envs or 256, a.B)
     value, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, a.steps, a.warmup)
     sample = (f"{n_envs} of {a.B} envs x T={a.T} per step (same update_epoch/mini-batch structure); "
-              f"oracle port of the reference CPU path (torch {cores} threads); the reference's own Ray runner "
+              f"oracle port of the reference CPU path (torch {cores} threads = usable host cores); the reference's own Ray runner "
               f"cannot be launched offline")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -256,8 +279,11 @@ def run_ours(a):
 
     # graph capture of the rollout happens on the 2nd call: make sure warm-up covers it
     warm = max(a.warmup, 3)
-    for _ in range(warm):
+    for i in range(warm):
+        t0 = time.perf_counter()
         run.run_iteration()
+        torch.cuda.synchronize()
+        log(f"warm-up iteration {i}: {time.perf_counter() - t0:.3f}s")
     barrier()
 
     # ---- device-resident timing (value) ----
@@ -268,6 +294,7 @@ def run_ours(a):
     launches0 = lib.rb200_launch_count()
     graph_nodes = run.rollout.graph_kernel_count
     barrier()
+    torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` captures the timed region only
     t_wall0 = time.perf_counter()
     ev[0].record()
     metrics = None
@@ -278,8 +305,10 @@ def run_ours(a):
         metrics = run.update_phase()
         ev[3 * i + 3].record()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     t_wall = time.perf_counter() - t_wall0
     total_ms = ev[0].elapsed_time(ev[3 * a.steps])
+    log(f"timed {a.steps} steps: {total_ms:.1f} ms")
     rollout_ms = sum((ev[3 * i].elapsed_time(ev[3 * i + 1])) for i in range(a.steps)) / a.steps
     launches = lib.rb200_launch_count() - launches0 + graph_nodes * a.steps
     clocks = sampler.stop() if sampler else None
@@ -331,6 +360,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_env_steps * e2e_steps / float(t.item())
+    log(f"e2e {e2e_steps} steps: {float(t.item()):.3f}s")
     metrics_bytes = 8 * 32
 
     line = {
@@ -367,13 +397,16 @@ def run_ours(a):
             "note": f"dense-GEMM flops of the update phase / update time; peak = {peaks['source']} bf16 sustained; "
                     "fp32 accumulate-exact path, tcgen05 3xTF32 path is the next step"}
         if not a.no_kernel_bench:
+            log("kernel rooflines ...")
             try:
                 line["roofline_hbm_kernels"] = kernel_rooflines(a, peaks, torch)
             except Exception as e:  # pragma: no cover
                 line["roofline_hbm_kernels"] = {"error": repr(e)}
         if not a.no_cpu_baseline and world == 1:
-            n_envs = min(a.cpu_envs, a.B)
+            n_envs = min(a.cpu_envs or 512, a.B)
+            log("cpu baseline ...")
             v, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, 1, 1)
+            log(f"cpu baseline iteration {mean_s:.2f}s {phases}")
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 iteration of {n_envs} of {a.B} envs x T={a.T}, same update structure; "
                                               f"oracle port of the reference CPU path, torch {cores} threads",

@@ -13,6 +13,8 @@
 // (/ mask) through an S-stage mbarrier ring in shared memory, newest timestep first.
 //
 // HBM traffic (algorithmic): r 4 + V 4 + done 1 (+ mask 1) read, adv 4 + ret 4 written = 17 B/step.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -30,13 +32,22 @@ struct __align__(128) Stage {
 };
 static_assert(sizeof(Stage) == 5120, "stage layout");
 
+// Statistics accumulator: fp32 partial sums over one tile of <= 16 values, folded into fp64 totals once per
+// tile (keeps the fp64 pipe and the F2F conversions out of the per-row instruction stream).
 struct Acc {
-  double n = 0, s = 0, ss = 0;
+  double s = 0, ss = 0;
+  float ts = 0.f, tss = 0.f;
+  int n = 0;
   __device__ __forceinline__ void add(float x) {
-    const double xd = (double)x;
-    n += 1.0;
-    s += xd;
-    ss += xd * xd;
+    n += 1;
+    ts += x;
+    tss = fmaf(x, x, tss);
+  }
+  __device__ __forceinline__ void fold() {
+    s += (double)ts;
+    ss += (double)tss;
+    ts = 0.f;
+    tss = 0.f;
   }
 };
 
@@ -63,7 +74,7 @@ __device__ __forceinline__ void gae_step(float r, float vt, float v_next, uint8_
 }
 
 __device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* stats) {
-  double v[6] = {a.n, a.s, a.ss, r.n, r.s, r.ss};
+  double v[6] = {(double)a.n, a.s, a.ss, (double)r.n, r.s, r.ss};
 #pragma unroll
   for (int k = 0; k < 6; ++k) v[k] = rb::warp_sum(v[k]);
   if ((threadIdx.x & 31) == 0) {
@@ -132,16 +143,14 @@ __global__ void __launch_bounds__(64) gae_tma_kernel(const __grid_constant__ CUt
   float v_next = (HAS_V && in_range) ? values[(size_t)T * B + col] : 0.0f;  // bootstrap row V[T]
   float g = 0.0f;
   Acc acc_a, acc_r;
-  for (int it = 0; it < n_iter; ++it) {
-    const int s = it % kS;
-    const uint32_t ph = (uint32_t)(it / kS) & 1u;
-    const int t0 = T - (it + 1) * kR;
-    rb::tma::mbar_wait(&full_bar[s], ph);
-    const Stage& st = stages[s];
+  // Full tiles are processed branch-free (so ptxas hoists the tile's shared-memory loads above the dependent
+  // fp32 chain); only a ragged first-in-time tile (T % kR != 0) takes the guarded path.
+  auto consume = [&](const Stage& st, int t0, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
     for (int rr = kR - 1; rr >= 0; --rr) {
       const int t = t0 + rr;
-      if (t >= 0) {  // warp-uniform
+      if (FULL || t >= 0) {  // warp-uniform; compiled out for full tiles
         const float r = st.r[rr][lane];
         const float vt = HAS_V ? st.v[rr][lane] : 0.0f;
         const uint8_t dn = st.d[rr][lane];
@@ -152,16 +161,30 @@ __global__ void __launch_bounds__(64) gae_tma_kernel(const __grid_constant__ CUt
           const size_t o = (size_t)t * B + col;
           adv[o] = ad;
           ret[o] = rt;
-          if (HAS_STATS) {
-            const bool valid = HAS_MASK ? (st.m[rr][lane] != 0) : true;
-            if (valid) {
-              acc_a.add(ad);
-              acc_r.add(rt);
-            }
+        }
+        if (HAS_STATS) {
+          const bool valid = in_range && (HAS_MASK ? (st.m[rr][lane] != 0) : true);
+          if (valid) {
+            acc_a.add(ad);
+            acc_r.add(rt);
           }
         }
       }
     }
+    if (HAS_STATS) {
+      acc_a.fold();
+      acc_r.fold();
+    }
+  };
+  for (int it = 0; it < n_iter; ++it) {
+    const int s = it % kS;
+    const uint32_t ph = (uint32_t)(it / kS) & 1u;
+    const int t0 = T - (it + 1) * kR;
+    rb::tma::mbar_wait(&full_bar[s], ph);
+    if (t0 >= 0)
+      consume(stages[s], t0, std::true_type{});
+    else
+      consume(stages[s], t0, std::false_type{});
     __syncwarp();
     if (lane == 0) rb::tma::mbar_arrive(&empty_bar[s]);
   }
@@ -213,6 +236,10 @@ __global__ void __launch_bounds__(32) gae_generic_kernel(const float* __restrict
             acc_r.add(rt);
           }
         }
+      }
+      if (HAS_STATS) {
+        acc_a.fold();
+        acc_r.fold();
       }
     }
   }

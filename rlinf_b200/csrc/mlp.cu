@@ -364,7 +364,9 @@ extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_d
   if (hidden != kH || act_dim > kMaxAct || value_dim > kMaxVal) return RB200_E_UNSUPPORTED;
   L->obs_dim = obs_dim; L->act_dim = act_dim; L->value_dim = value_dim; L->hidden = hidden;
   int64_t o = 0;
-  auto take = [&](int64_t n) { const int64_t at = o; o += n; return at; };
+  // every tensor starts on a 16-byte boundary (vector loads, TMA); the <=3 pad floats between tensors stay
+  // zero forever (zero grad, zero Adam state, decay of zero)
+  auto take = [&](int64_t n) { o = (o + 3) & ~int64_t(3); const int64_t at = o; o += n; return at; };
   // named_parameters() order of the reference MLPPolicy: own Parameter first, then children in construction
   // order (value_head, backbone, actor_mean) - mlp_policy.py:28-105
   L->logstd = take(act_dim);
@@ -376,7 +378,7 @@ extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_d
   L->bw1 = take((int64_t)hidden * hidden); L->bb1 = take(hidden);
   L->bw2 = take((int64_t)hidden * hidden); L->bb2 = take(hidden);
   L->mw = take((int64_t)act_dim * hidden); L->mb = take(act_dim);
-  L->total = o;
+  L->total = (o + 3) & ~int64_t(3);
   return RB200_OK;
 }
 

@@ -84,6 +84,7 @@ class MLPPolicy:
                 segs[-1][1] = end
             else:
                 segs.append([kind, end])
+        segs[-1][1] = int(self.layout.total)  # trailing alignment pad belongs to the last group
         return segs
 
     def reset_parameters(self, seed: Optional[int] = None):

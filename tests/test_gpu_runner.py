@@ -132,5 +132,7 @@ def test_host_batch_e2e_equals_device_batch():
     host = _cpu_batch(a.buffer.as_batch())
     ma = a.update_phase()
     mb = b.update_phase(batch=host)
-    assert torch.equal(a.actor.model.flat_params, b.actor.model.flat_params)
-    assert ma == mb
+    # weight-gradient partial sums use float atomics (order not deterministic): equal to rounding, not bitwise
+    torch.testing.assert_close(a.actor.model.flat_params, b.actor.model.flat_params, rtol=1e-5, atol=1e-7)
+    for k in ma:
+        np.testing.assert_allclose(ma[k], mb[k], rtol=1e-4, atol=1e-7, err_msg=k)
