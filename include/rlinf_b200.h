@@ -220,36 +220,49 @@ typedef struct rb200_mlp_layout {
 
 int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_dim, int value_dim, int hidden);
 
-/* scratch sizes (floats) for n rows */
+/* scratch sizes (floats) for n rows: `acts` and `work` of forward/backward/sample/value each need this many */
 int64_t rb200_mlp_fwd_scratch_floats(const rb200_mlp_layout* L, int64_t n);
+
+/* Tensor-core operand cache: exact-TF32 (hi, lo) copies (and transposes) of the hidden-layer weights.
+ * rb200_mlp_wsplit_floats() floats; refresh with rb200_mlp_prepare_weights() after every parameter update.
+ * Passing wsplit == NULL to the calls below selects the fp32 SIMT GEMMs for every layer. */
+int64_t rb200_mlp_wsplit_floats(const rb200_mlp_layout* L);
+int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float* params, float* wsplit,
+                              rb200_stream_t stream);
 
 /* Forward for training: states [n,obs] (row i at idx?idx[i]:i), action [n,act] (same gather).
  * Writes logprobs [n,act], entropy [n,act] (NULL ok), values [n,value_dim] (NULL ok) and keeps
- * the activations needed by backward in `acts` (rb200_mlp_fwd_scratch_floats floats). */
-int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* states,
-                      const float* action, const int64_t* idx, int64_t n, float* logprobs,
-                      float* entropy, float* values, float* acts, rb200_stream_t stream);
+ * the activations needed by backward in `acts`. Hidden layers run on tcgen05 (3xTF32) when wsplit is given
+ * and the layer's K is a multiple of 32 (layer 1 additionally needs idx == NULL). */
+int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                      const float* states, const float* action, const int64_t* idx, int64_t n,
+                      float* logprobs, float* entropy, float* values, float* acts, float* work,
+                      rb200_stream_t stream);
 
 /* Backward: given d_logprobs [n,act], d_entropy [n,act] or NULL, d_values [n,value_dim] or NULL,
- * ACCUMULATES (+=) parameter gradients into grads (flat, same layout). `acts` from forward;
- * `work` is scratch of the same size as acts. */
-int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* states,
-                       const float* action, const int64_t* idx, int64_t n,
+ * ACCUMULATES (+=) parameter gradients into grads (flat, same layout). `acts` from forward. */
+int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                       const float* states, const float* action, const int64_t* idx, int64_t n,
                        const float* d_logprobs, const float* d_entropy, const float* d_values,
                        const float* acts, float* work, float* grads, rb200_stream_t stream);
 
 /* Rollout step (inference): mean/value forward, action = mean + exp(logstd)*noise where noise is
- * either supplied ([n,act], parity mode) or drawn from Philox(seed, offset + *counter_dev) (noise == NULL; counter_dev may be NULL);
- * writes action [n,act], logprobs [n,act], values [n,value_dim]. */
-int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* states,
-                     const float* noise, uint64_t seed, uint64_t offset, const uint64_t* counter_dev,
-                     int64_t n, float* action, float* logprobs, float* values, float* work,
-                     rb200_stream_t stream);
+ * either supplied ([n,act], parity mode) or drawn from Philox(seed, offset + *counter_dev) (noise == NULL;
+ * counter_dev may be NULL); writes action [n,act], logprobs [n,act], values [n,value_dim]. */
+int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                     const float* states, const float* noise, uint64_t seed, uint64_t offset,
+                     const uint64_t* counter_dev, int64_t n, float* action, float* logprobs, float* values,
+                     float* work, rb200_stream_t stream);
+
+/* 3xTF32 tensor-core GEMM building block of the MLP towers (unit-test entry):
+ * C[M,256] = A[M,K] . B[256,K]^T, fp32 in/out, K % 32 == 0; `work` = 2*M*K + 512*K floats. */
+int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M, int K, float* work,
+                  rb200_stream_t stream);
 
 /* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
  * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */
-int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* states, int64_t n,
-                    float* values, float* work, rb200_stream_t stream);
+int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                    const float* states, int64_t n, float* values, float* work, rb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Rollout-side helpers (device-resident rollout loop; replaces the per-chunk-step Channel hops with

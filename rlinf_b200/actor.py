@@ -256,3 +256,4 @@ class EmbodiedActor:
             rollout_params.copy_(self.model.flat_params)
         if self._world_size > 1 and self.cfg.runner.get("broadcast_params", True):
             dist.broadcast(self.model.flat_params, src=src, group=self.pg)
+        self.model.mark_params_changed()

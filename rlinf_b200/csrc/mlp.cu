@@ -4,33 +4,38 @@
 // ValueHead, rlinf/models/embodiment/modules/value_head.py:18-67 (3x256 tanh MLP -> value_dim, last layer
 // without bias); backward = what autograd derives from them.
 //
-// This translation unit holds the fp32 SIMT GEMM path (exact fp32 accumulation: parity reference for the
-// tensor-core path) plus the fused head kernels (mean/value heads + Normal log-prob/entropy epilogue, and
-// their backward).  Activations are kept as tanh outputs (tanh' = 1 - h^2), 6 x [n,256] floats.
+// Hidden-layer GEMMs run on the tensor cores (tc_gemm.cu: tcgen05 kind::tf32 with 3xTF32 compensation, fp32-level
+// accuracy) whenever the operand shapes allow TMA (K % 32 == 0, no row gather); the fp32 SIMT GEMM (sgemm.cuh)
+// covers the remaining shapes and the weight-gradient GEMMs (reduction over samples).  All activations and
+// activation-gradients are stored as exact-TF32 (hi, lo) pairs, x = hi + lo, so they can be fed to the tensor cores
+// without a conversion pass: 12 x [n,256] floats of tanh outputs (tanh' = 1 - h^2) per forward.
+// The heads (256 -> act mean, 256 -> value) are fused with the Normal log-prob / entropy epilogue and their backward.
 #include <curand_kernel.h>
 
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
 using namespace rb::gemm;
 
 // out[n] += sum_m Z[m][n]   (bias gradients); Z is [M, N] with N <= 1024
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, float* __restrict__ out, int64_t M,
-                                                     int N, int64_t rows_per_block) {
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, const float* __restrict__ Z2,
+                                                     float* __restrict__ out, int64_t M, int N,
+                                                     int64_t rows_per_block) {
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int64_t r = r0;
     for (; r + 3 < r1; r += 4) {
-      s0 += Z[r * N + n];
-      s1 += Z[(r + 1) * N + n];
-      s2 += Z[(r + 2) * N + n];
-      s3 += Z[(r + 3) * N + n];
+      s0 += Z[r * N + n] + Z2[r * N + n];
+      s1 += Z[(r + 1) * N + n] + Z2[(r + 1) * N + n];
+      s2 += Z[(r + 2) * N + n] + Z2[(r + 2) * N + n];
+      s3 += Z[(r + 3) * N + n] + Z2[(r + 3) * N + n];
     }
-    for (; r < r1; ++r) s0 += Z[r * N + n];
+    for (; r < r1; ++r) s0 += Z[r * N + n] + Z2[r * N + n];
     atomicAdd(&out[n], (s0 + s1) + (s2 + s3));
   }
 }
@@ -43,9 +48,25 @@ constexpr int kMaxAct = 32;
 constexpr int kMaxVal = 8;
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
 
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(__fsub_rn(x, hi)) & 0xffffe000u);
+}
+__device__ __forceinline__ void store_split(float* hi, float* lo, int64_t off, float4 v) {
+  float4 h, l;
+  split1(v.x, h.x, l.x);
+  split1(v.y, h.y, l.y);
+  split1(v.z, h.z, l.z);
+  split1(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = l;
+}
+
 struct HeadFwdArgs {
-  const float* h3;      // [n,256] backbone features
-  const float* g3;      // [n,256] value features (may be null -> no values)
+  const float* h3;      // [n,256] backbone features, hi part
+  const float* h3l;     //         lo part
+  const float* g3;      // [n,256] value features hi (may be null -> no values)
+  const float* g3l;
   const float* mw;      // [act,256]
   const float* mb;      // [act]
   const float* logstd;  // [act]
@@ -75,8 +96,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 h0 = *reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4);
-    const float4 h1 = *reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4);
+    const float4 h0 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4),
+                           *reinterpret_cast<const float4*>(p.h3l + row * kH + lane * 4));
+    const float4 h1 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4),
+                           *reinterpret_cast<const float4*>(p.h3l + row * kH + 128 + lane * 4));
     float my_mean = 0.f;
     for (int a = 0; a < p.act; ++a) {
       const float4 w0 = *reinterpret_cast<const float4*>(s_mw + a * kH + lane * 4);
@@ -113,8 +136,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
       if (p.mean_out) p.mean_out[row * p.act + lane] = my_mean;
     }
     if (p.g3 && p.values) {
-      const float4 g0 = *reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4);
-      const float4 g1 = *reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4);
+      const float4 g0 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4),
+                             *reinterpret_cast<const float4*>(p.g3l + row * kH + lane * 4));
+      const float4 g1 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4),
+                             *reinterpret_cast<const float4*>(p.g3l + row * kH + 128 + lane * 4));
       for (int c = 0; c < p.vdim; ++c) {
         const float4 w0 = *reinterpret_cast<const float4*>(s_vw + c * kH + lane * 4);
         const float4 w1 = *reinterpret_cast<const float4*>(s_vw + c * kH + 128 + lane * 4);
@@ -128,8 +153,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
 }
 
 struct HeadBwdArgs {
-  const float* h3;
+  const float* h3;   // hi / lo parts of the layer-3 activations
+  const float* h3l;
   const float* g3;
+  const float* g3l;
   const float* mean;    // [n,act] saved by forward
   const float* mw;
   const float* logstd;
@@ -139,8 +166,10 @@ struct HeadBwdArgs {
   const float* d_logprobs;  // [n,act]
   const float* d_entropy;   // [n,act] or null
   const float* d_values;    // [n,vdim] or null
-  float* dz3;               // [n,256] out: grad wrt backbone layer-3 pre-activation
+  float* dz3;               // [n,256] out: grad wrt backbone layer-3 pre-activation (hi, lo)
+  float* dz3l;
   float* dy3;               // [n,256] out: grad wrt value layer-3 pre-activation (if d_values)
+  float* dy3l;
   float* g_mw;              // [act,256] +=
   float* g_mb;              // [act] +=
   float* g_logstd;          // [act] +=
@@ -183,8 +212,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) rv[c][j] = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 h0 = *reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4);
-    const float4 h1 = *reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4);
+    const float4 h0 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4),
+                           *reinterpret_cast<const float4*>(p.h3l + row * kH + lane * 4));
+    const float4 h1 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4),
+                           *reinterpret_cast<const float4*>(p.h3l + row * kH + 128 + lane * 4));
     float dmu = 0.f;
     if (lane < p.act) {
       const int64_t src = p.idx ? p.idx[row] : row;
@@ -226,12 +257,14 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
     o0.z = dh0.z * (1.f - h0.z * h0.z); o0.w = dh0.w * (1.f - h0.w * h0.w);
     o1.x = dh1.x * (1.f - h1.x * h1.x); o1.y = dh1.y * (1.f - h1.y * h1.y);
     o1.z = dh1.z * (1.f - h1.z * h1.z); o1.w = dh1.w * (1.f - h1.w * h1.w);
-    *reinterpret_cast<float4*>(p.dz3 + row * kH + lane * 4) = o0;
-    *reinterpret_cast<float4*>(p.dz3 + row * kH + 128 + lane * 4) = o1;
+    store_split(p.dz3, p.dz3l, row * kH + lane * 4, o0);
+    store_split(p.dz3, p.dz3l, row * kH + 128 + lane * 4, o1);
 
     if (has_v) {
-      const float4 g0 = *reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4);
-      const float4 g1 = *reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4);
+      const float4 g0 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4),
+                             *reinterpret_cast<const float4*>(p.g3l + row * kH + lane * 4));
+      const float4 g1 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4),
+                             *reinterpret_cast<const float4*>(p.g3l + row * kH + 128 + lane * 4));
       float4 dg0 = make_float4(0.f, 0.f, 0.f, 0.f), dg1 = dg0;
 #pragma unroll
       for (int c = 0; c < (REG ? 2 : kMaxVal); ++c) {
@@ -258,8 +291,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
       q0.z = dg0.z * (1.f - g0.z * g0.z); q0.w = dg0.w * (1.f - g0.w * g0.w);
       q1.x = dg1.x * (1.f - g1.x * g1.x); q1.y = dg1.y * (1.f - g1.y * g1.y);
       q1.z = dg1.z * (1.f - g1.z * g1.z); q1.w = dg1.w * (1.f - g1.w * g1.w);
-      *reinterpret_cast<float4*>(p.dy3 + row * kH + lane * 4) = q0;
-      *reinterpret_cast<float4*>(p.dy3 + row * kH + 128 + lane * 4) = q1;
+      store_split(p.dy3, p.dy3l, row * kH + lane * 4, q0);
+      store_split(p.dy3, p.dy3l, row * kH + 128 + lane * 4, q1);
     }
   }
   if (REG) {
@@ -305,55 +338,99 @@ int head_grid(int64_t n) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-// three hidden layers of one tower: X -> H1 -> H2 -> H3
-int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, const float* w0, const float* b0,
-                  const float* w1, const float* b1, const float* w2, const float* b2, float* H1, float* H2, float* H3,
-                  cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------------------
+// Towers.  Activation / gradient tensors are (hi, lo) pairs: pointer `x` = hi part, `x + n*256` = lo part.
+// ---------------------------------------------------------------------------------------------------------
+struct TowerW {           // fp32 weights (SIMT path, wgrad)
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+};
+struct TowerWS {          // exact-TF32 (hi, lo) copies for the tensor cores (null => SIMT everywhere)
+  const float *w0h, *w0l, *w1h, *w1l, *w2h, *w2l;   // [256,in] as stored (forward:  X . W^T)
+  const float *w1th, *w1tl, *w2th, *w2tl;           // transposed [in=256, out=256] (dgrad: dZ . W)
+};
+
+// one hidden layer forward: out(hi,lo) = split(tanh(in . W^T + b))
+int layer_forward(const float* in_hi, const float* in_lo, const int64_t* idx, int64_t n, int in_dim, const float* w,
+                  const float* b, const float* wh, const float* wl, float* out, float* xsplit, cudaStream_t st) {
+  float* out_lo = out + n * kH;
+  const bool tc_ok = wh != nullptr && idx == nullptr && (in_dim % rb::tc::BK == 0);
+  if (tc_ok) {
+    const float *ah = in_hi, *al = in_lo;
+    if (in_lo == nullptr) {  // raw fp32 input (layer 1): split it first
+      int e = rb::tc::split(in_hi, xsplit, xsplit + n * in_dim, n * in_dim, st);
+      if (e) return e;
+      ah = xsplit;
+      al = xsplit + n * in_dim;
+    }
+    rb::tc::Params p{};
+    p.M = n; p.K = in_dim; p.bias = b; p.c_hi = out; p.c_lo = out_lo; p.epi = rb::tc::EPI_BIAS_TANH_SPLIT;
+    return rb::tc::launch(ah, al, wh, wl, p, st);
+  }
   GemmArgs g{};
   g.M = n; g.N = kH; g.ldc = kH; g.k_per_split = 1 << 30;
-  g.A = X; g.lda = in_dim; g.a_rows = idx; g.B = w0; g.ldb = in_dim; g.K = in_dim; g.bias = b0; g.C = H1;
+  g.A = in_hi; g.A2 = in_lo; g.lda = in_dim; g.a_rows = idx; g.B = w; g.ldb = in_dim; g.K = in_dim; g.bias = b; g.C = out;
   int e = launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
   if (e) return e;
-  g.A = H1; g.lda = kH; g.a_rows = nullptr; g.B = w1; g.ldb = kH; g.K = kH; g.bias = b1; g.C = H2;
-  e = launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
-  if (e) return e;
-  g.A = H2; g.B = w2; g.bias = b2; g.C = H3;
-  return launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
+  return rb::tc::split(out, out, out_lo, n * kH, st);  // in place: hi overwrites the fp32 value it was read from
 }
 
-// backward through the three hidden layers of one tower, given dZ3 (grad wrt layer-3 pre-activation).
-// buffers: dZ3 is overwritten-free; tmpA/tmpB are [n,256] scratch.
-int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, const float* w1, const float* w2,
+// X -> H1 -> H2 -> H3 (each [2][n,256])
+int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
+                  float* H1, float* H2, float* H3, float* xsplit, cudaStream_t st) {
+  int e = layer_forward(X, nullptr, idx, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr, ws ? ws->w0l : nullptr, H1,
+                        xsplit, st);
+  if (e) return e;
+  e = layer_forward(H1, H1 + n * kH, nullptr, n, kH, w.w1, w.b1, ws ? ws->w1h : nullptr, ws ? ws->w1l : nullptr, H2,
+                    xsplit, st);
+  if (e) return e;
+  return layer_forward(H2, H2 + n * kH, nullptr, n, kH, w.w2, w.b2, ws ? ws->w2h : nullptr, ws ? ws->w2l : nullptr, H3,
+                       xsplit, st);
+}
+
+// backward through the three hidden layers of one tower, given dZ3 (hi,lo). tmpA/tmpB: [2][n,256] scratch.
+int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
                    const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB, float* g_w0,
                    float* g_b0, float* g_w1, float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
   const int64_t rows_per_split = 4096;
   const int splits = (int)((n + rows_per_split - 1) / rows_per_split);
-  const int64_t cs_rows = 1024;
+  const int64_t cs_rows = 128;
   const int cs_blocks = (int)((n + cs_rows - 1) / cs_rows);
+  const int64_t L = n * kH;  // offset of the lo part
   int e;
-  auto wgrad = [&](const float* dZ, const float* Hin, const int64_t* in_rows, int in_ld, float* gw, float* gb) -> int {
-    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
+  auto wgrad = [&](const float* dZ, const float* Hin, const float* Hin_lo, const int64_t* in_rows, int in_ld,
+                   float* gw, float* gb) -> int {
+    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]      (fp32 SIMT, split over samples, atomics)
     GemmArgs g{};
-    g.A = dZ; g.lda = kH; g.B = Hin; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw; g.ldc = in_ld;
-    g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
+    g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = Hin; g.B2 = Hin_lo; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw;
+    g.ldc = in_ld; g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
     int ee = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(g, splits, st);
     if (ee) return ee;
-    colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, gb, n, kH, cs_rows); rb::count_launch();
+    colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows);
+    rb::count_launch();
     cudaError_t ce = cudaPeekAtLastError();
     return ce == cudaSuccess ? 0 : (int)ce;
   };
-  auto dgrad = [&](const float* dZ, const float* W, const float* Hprev, float* out) -> int {
-    // out[n,256] = (dZ [n,256] . W [256,256]) * (1 - Hprev^2)
+  auto dgrad = [&](const float* dZ, const float* W, const float* Wth, const float* Wtl, const float* Hprev,
+                   float* out) -> int {
+    // out(hi,lo) = split( (dZ . W) * (1 - Hprev^2) )
+    if (Wth) {
+      rb::tc::Params p{};
+      p.M = n; p.K = kH; p.h_hi = Hprev; p.h_lo = Hprev + L; p.c_hi = out; p.c_lo = out + L;
+      p.epi = rb::tc::EPI_TANHGRAD_SPLIT;
+      return rb::tc::launch(dZ, dZ + L, Wth, Wtl, p, st);
+    }
     GemmArgs g{};
-    g.A = dZ; g.lda = kH; g.B = W; g.ldb = kH; g.C = out; g.ldc = kH; g.aux = Hprev; g.ldaux = kH;
-    g.M = n; g.N = kH; g.K = kH; g.k_per_split = 1 << 30;
-    return launch_gemm<A_KCONTIG, B_NCONTIG, EPI_TANHGRAD>(g, 1, st);
+    g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = W; g.ldb = kH; g.C = out; g.ldc = kH; g.aux = Hprev; g.aux2 = Hprev + L;
+    g.ldaux = kH; g.M = n; g.N = kH; g.K = kH; g.k_per_split = 1 << 30;
+    int ee = launch_gemm<A_KCONTIG, B_NCONTIG, EPI_TANHGRAD>(g, 1, st);
+    if (ee) return ee;
+    return rb::tc::split(out, out, out + L, L, st);
   };
-  if ((e = wgrad(dZ3, H2, nullptr, kH, g_w2, g_b2))) return e;
-  if ((e = dgrad(dZ3, w2, H2, tmpA))) return e;        // dZ2
-  if ((e = wgrad(tmpA, H1, nullptr, kH, g_w1, g_b1))) return e;
-  if ((e = dgrad(tmpA, w1, H1, tmpB))) return e;        // dZ1
-  return wgrad(tmpB, X, idx, in_dim, g_w0, g_b0);
+  if ((e = wgrad(dZ3, H2, H2 + L, nullptr, kH, g_w2, g_b2))) return e;
+  if ((e = dgrad(dZ3, w.w2, ws ? ws->w2th : nullptr, ws ? ws->w2tl : nullptr, H2, tmpA))) return e;  // dZ2
+  if ((e = wgrad(tmpA, H1, H1 + L, nullptr, kH, g_w1, g_b1))) return e;
+  if ((e = dgrad(tmpA, w.w1, ws ? ws->w1th : nullptr, ws ? ws->w1tl : nullptr, H1, tmpB))) return e;  // dZ1
+  return wgrad(tmpB, X, nullptr, idx, in_dim, g_w0, g_b0);
 }
 
 }  // namespace
@@ -382,10 +459,22 @@ extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_d
   return RB200_OK;
 }
 
-// acts layout (floats): H1 H2 H3 G1 G2 G3 (each n*256) | mean (n*act)
+// acts layout (floats): H1 H2 H3 G1 G2 G3, each a (hi, lo) pair of [n,256] | mean [n,act]
+// work layout: 6 gradient pairs of [n,256] | split copy of the input states 2*[n,obs]
+static inline int64_t pair_floats(int64_t n) { return 2 * n * kH; }
+
 extern "C" int64_t rb200_mlp_fwd_scratch_floats(const rb200_mlp_layout* L, int64_t n) {
   if (!L || n <= 0) return 0;
-  return 6 * n * kH + n * L->act_dim + 64;
+  return 6 * pair_floats(n) + n * L->act_dim + 2 * n * L->obs_dim + 64;
+}
+
+// wsplit layout (floats), per tower (value tower first, then backbone), every block 16-byte aligned:
+//   w0h w0l [256*obs] | w1h w1l w2h w2l [65536 each] | w1th w1tl w2th w2tl [65536 each]
+static inline int64_t wsplit_tower_floats(int obs) { return 2ll * kH * obs + 8ll * kH * kH; }
+
+extern "C" int64_t rb200_mlp_wsplit_floats(const rb200_mlp_layout* L) {
+  if (!L) return 0;
+  return 2 * wsplit_tower_floats(L->obs_dim);
 }
 
 static int check_layout(const rb200_mlp_layout* L) {
@@ -395,52 +484,103 @@ static int check_layout(const rb200_mlp_layout* L) {
   return RB200_OK;
 }
 
-extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* states,
-                                 const float* action, const int64_t* idx, int64_t n, float* logprobs, float* entropy,
-                                 float* values, float* acts, rb200_stream_t stream) {
+namespace {
+TowerW tower_w(const rb200_mlp_layout* L, const float* P, bool value) {
+  TowerW w;
+  if (value) {
+    w.w0 = P + L->vw0; w.b0 = P + L->vb0; w.w1 = P + L->vw1; w.b1 = P + L->vb1; w.w2 = P + L->vw2; w.b2 = P + L->vb2;
+  } else {
+    w.w0 = P + L->bw0; w.b0 = P + L->bb0; w.w1 = P + L->bw1; w.b1 = P + L->bb1; w.w2 = P + L->bw2; w.b2 = P + L->bb2;
+  }
+  return w;
+}
+TowerWS tower_ws(const rb200_mlp_layout* L, const float* ws, bool value) {
+  const float* b = ws + (value ? 0 : wsplit_tower_floats(L->obs_dim));
+  const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;
+  TowerWS t;
+  t.w0h = b; t.w0l = b + n0;
+  const float* q = b + 2 * n0;
+  t.w1h = q; t.w1l = q + nn; t.w2h = q + 2 * nn; t.w2l = q + 3 * nn;
+  t.w1th = q + 4 * nn; t.w1tl = q + 5 * nn; t.w2th = q + 6 * nn; t.w2tl = q + 7 * nn;
+  return t;
+}
+}  // namespace
+
+// Refresh the exact-TF32 (hi, lo) weight copies the tensor-core GEMMs read. Call after every parameter update
+// (once per optimiser step / once per rollout); 2 x 10 tiny kernels.
+extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float* params, float* wsplit,
+                                         rb200_stream_t stream) {
   int e = check_layout(L);
   if (e) return e;
-  if (!params || !states || !action || !logprobs || !acts) return RB200_E_NULL;
+  if (!params || !wsplit) return RB200_E_NULL;
+  cudaStream_t st = rb::as_stream(stream);
+  for (int v = 0; v < 2; ++v) {
+    if (v == 0 && L->value_dim == 0) continue;
+    const TowerW w = tower_w(L, params, v == 0);
+    const TowerWS t = tower_ws(L, wsplit, v == 0);
+    const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;
+    if ((e = rb::tc::split(w.w0, const_cast<float*>(t.w0h), const_cast<float*>(t.w0l), n0, st))) return e;
+    if ((e = rb::tc::split(w.w1, const_cast<float*>(t.w1h), const_cast<float*>(t.w1l), nn, st))) return e;
+    if ((e = rb::tc::split(w.w2, const_cast<float*>(t.w2h), const_cast<float*>(t.w2l), nn, st))) return e;
+    if ((e = rb::tc::split_transpose(w.w1, const_cast<float*>(t.w1th), const_cast<float*>(t.w1tl), kH, kH, st))) return e;
+    if ((e = rb::tc::split_transpose(w.w2, const_cast<float*>(t.w2th), const_cast<float*>(t.w2tl), kH, kH, st))) return e;
+  }
+  return RB200_OK;
+}
+
+extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                                 const float* states, const float* action, const int64_t* idx, int64_t n,
+                                 float* logprobs, float* entropy, float* values, float* acts, float* work,
+                                 rb200_stream_t stream) {
+  int e = check_layout(L);
+  if (e) return e;
+  if (!params || !states || !action || !logprobs || !acts || !work) return RB200_E_NULL;
   if (n <= 0) return RB200_E_SHAPE;
   if (values && L->value_dim == 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  float *H1 = acts, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH, *G3 = G2 + n * kH;
-  float* mean = G3 + n * kH;
+  const int64_t PF = pair_floats(n);
+  float *H1 = acts, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
+  float* mean = G3 + PF;
+  float* xsplit = work + 6 * PF;
   const float* P = params;
-  if ((e = tower_forward(states, idx, n, L->obs_dim, P + L->bw0, P + L->bb0, P + L->bw1, P + L->bb1, P + L->bw2,
-                         P + L->bb2, H1, H2, H3, st)))
+  const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
+  const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
+  if ((e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3, xsplit,
+                         st)))
     return e;
-  if (values && (e = tower_forward(states, idx, n, L->obs_dim, P + L->vw0, P + L->vb0, P + L->vw1, P + L->vb1,
-                                   P + L->vw2, P + L->vb2, G1, G2, G3, st)))
+  if (values &&
+      (e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
     return e;
   HeadFwdArgs h{};
-  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb; h.logstd = P + L->logstd;
-  h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.sample_mode = 0; h.mean_out = mean; h.logprobs = logprobs;
-  h.entropy = entropy; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
+  h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.sample_mode = 0; h.mean_out = mean;
+  h.logprobs = logprobs; h.entropy = entropy; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
   const size_t smem = sizeof(float) * (size_t)(L->act_dim + L->value_dim) * kH;
-  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h); rb::count_launch();
+  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h);
+  rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
-extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* states,
-                                  const float* action, const int64_t* idx, int64_t n, const float* d_logprobs,
-                                  const float* d_entropy, const float* d_values, const float* acts, float* work,
-                                  float* grads, rb200_stream_t stream) {
+extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                                  const float* states, const float* action, const int64_t* idx, int64_t n,
+                                  const float* d_logprobs, const float* d_entropy, const float* d_values,
+                                  const float* acts, float* work, float* grads, rb200_stream_t stream) {
   int e = check_layout(L);
   if (e) return e;
   if (!params || !states || !action || !d_logprobs || !acts || !work || !grads) return RB200_E_NULL;
   if (n <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  const float *H1 = acts, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH,
-              *G3 = G2 + n * kH;
-  const float* mean = G3 + n * kH;
-  float *dZ3 = work, *tA = dZ3 + n * kH, *tB = tA + n * kH, *dY3 = tB + n * kH, *uA = dY3 + n * kH, *uB = uA + n * kH;
+  const int64_t PF = pair_floats(n);
+  const float *H1 = acts, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
+  const float* mean = G3 + PF;
+  float *dZ3 = work, *tA = dZ3 + PF, *tB = tA + PF, *dY3 = tB + PF, *uA = dY3 + PF, *uB = uA + PF;
   const float* P = params;
   float* G = grads;
   HeadBwdArgs h{};
-  h.h3 = H3; h.g3 = G3; h.mean = mean; h.mw = P + L->mw; h.logstd = P + L->logstd; h.vw3 = P + L->vw3;
-  h.action = action; h.idx = idx; h.d_logprobs = d_logprobs; h.d_entropy = d_entropy; h.d_values = d_values;
-  h.dz3 = dZ3; h.dy3 = dY3; h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
+  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = G3; h.g3l = G3 + n * kH; h.mean = mean; h.mw = P + L->mw;
+  h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.d_logprobs = d_logprobs;
+  h.d_entropy = d_entropy; h.d_values = d_values; h.dz3 = dZ3; h.dz3l = dZ3 + n * kH; h.dy3 = dY3; h.dy3l = dY3 + n * kH;
+  h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
   h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
   const size_t smem = sizeof(float) * ((size_t)2 * (L->act_dim + L->value_dim) * kH + 64);
   const bool reg = L->act_dim <= 8 && L->value_dim <= 2;
@@ -458,50 +598,62 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
     cudaError_t ce = cudaPeekAtLastError();
     if (ce != cudaSuccess) return (int)ce;
   }
-  if ((e = tower_backward(states, idx, n, L->obs_dim, P + L->bw1, P + L->bw2, H1, H2, dZ3, tA, tB, G + L->bw0,
-                          G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
+  const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
+  const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
+  if ((e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, dZ3, tA,
+                          tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
     return e;
   if (d_values &&
-      (e = tower_backward(states, idx, n, L->obs_dim, P + L->vw1, P + L->vw2, G1, G2, dY3, uA, uB, G + L->vw0,
-                          G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
+      (e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, dY3, uA, uB,
+                          G + L->vw0, G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
     return e;
   return RB200_OK;
 }
 
-extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* states,
-                                const float* noise, uint64_t seed, uint64_t offset, const uint64_t* counter_dev,
-                                int64_t n, float* action, float* logprobs, float* values, float* work,
-                                rb200_stream_t stream) {
+// work: 6 activation pairs + split input copy = rb200_mlp_fwd_scratch_floats(L, n) floats is always enough
+extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                                const float* states, const float* noise, uint64_t seed, uint64_t offset,
+                                const uint64_t* counter_dev, int64_t n, float* action, float* logprobs, float* values,
+                                float* work, rb200_stream_t stream) {
   int e = check_layout(L);
   if (e) return e;
   if (!params || !states || !action || !logprobs || !work) return RB200_E_NULL;
   if (n <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  float *H1 = work, *H2 = H1 + n * kH, *H3 = H2 + n * kH, *G1 = H3 + n * kH, *G2 = G1 + n * kH, *G3 = G2 + n * kH;
+  const int64_t PF = pair_floats(n);
+  float *H1 = work, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
+  float* xsplit = G3 + PF;
   const float* P = params;
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, P + L->bw0, P + L->bb0, P + L->bw1, P + L->bb1, P + L->bw2,
-                         P + L->bb2, H1, H2, H3, st)))
+  const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
+  const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
+  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3,
+                         xsplit, st)))
     return e;
-  if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, P + L->vw0, P + L->vb0, P + L->vw1, P + L->vb1,
-                                   P + L->vw2, P + L->vb2, G1, G2, G3, st)))
+  if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2,
+                                   G3, xsplit, st)))
     return e;
   HeadFwdArgs h{};
-  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb; h.logstd = P + L->logstd;
-  h.vw3 = P + L->vw3; h.noise = noise; h.seed = seed; h.offset = offset; h.counter = counter_dev; h.sample_mode = 1; h.action_out = action;
-  h.logprobs = logprobs; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
+  h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.noise = noise; h.seed = seed; h.offset = offset;
+  h.counter = counter_dev; h.sample_mode = 1; h.action_out = action; h.logprobs = logprobs; h.values = values; h.n = n;
+  h.act = L->act_dim; h.vdim = L->value_dim;
   const size_t smem = sizeof(float) * (size_t)(L->act_dim + L->value_dim) * kH;
-  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h); rb::count_launch();
+  head_fwd_kernel<<<head_grid(n), 256, smem, st>>>(h);
+  rb::count_launch();
   RB_RETURN_LAUNCH();
 }
 
 // value tower + last linear layer only (no bias on the last layer: value_head.py:46)
 namespace {
-__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ g3, const float* __restrict__ vw3,
-                                                         float* __restrict__ values, int64_t n, int vdim) {
+__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ g3, const float* __restrict__ g3l,
+                                                         const float* __restrict__ vw3, float* __restrict__ values,
+                                                         int64_t n, int vdim) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 g0 = *reinterpret_cast<const float4*>(g3 + row * kH + lane * 4);
-    const float4 g1 = *reinterpret_cast<const float4*>(g3 + row * kH + 128 + lane * 4);
+    const float4 g0 = add4(*reinterpret_cast<const float4*>(g3 + row * kH + lane * 4),
+                           *reinterpret_cast<const float4*>(g3l + row * kH + lane * 4));
+    const float4 g1 = add4(*reinterpret_cast<const float4*>(g3 + row * kH + 128 + lane * 4),
+                           *reinterpret_cast<const float4*>(g3l + row * kH + 128 + lane * 4));
     for (int c = 0; c < vdim; ++c) {
       const float4 w0 = *reinterpret_cast<const float4*>(vw3 + c * kH + lane * 4);
       const float4 w1 = *reinterpret_cast<const float4*>(vw3 + c * kH + 128 + lane * 4);
@@ -514,18 +666,22 @@ __global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict
 }
 }  // namespace
 
-extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* states, int64_t n,
-                               float* values, float* work, rb200_stream_t stream) {
+// work: 3 activation pairs + split input copy
+extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,
+                               const float* states, int64_t n, float* values, float* work, rb200_stream_t stream) {
   int e = check_layout(L);
   if (e) return e;
   if (!params || !states || !values || !work) return RB200_E_NULL;
   if (n <= 0 || L->value_dim <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  float *G1 = work, *G2 = G1 + n * kH, *G3 = G2 + n * kH;
-  const float* P = params;
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, P + L->vw0, P + L->vb0, P + L->vw1, P + L->vb1, P + L->vw2,
-                         P + L->vb2, G1, G2, G3, st)))
+  const int64_t PF = pair_floats(n);
+  float *G1 = work, *G2 = G1 + PF, *G3 = G2 + PF;
+  float* xsplit = G3 + PF;
+  const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
+  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, params, true), wsplit ? &vws : nullptr, G1, G2, G3,
+                         xsplit, st)))
     return e;
-  value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, P + L->vw3, values, n, L->value_dim); rb::count_launch();
+  value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, G3 + n * kH, params + L->vw3, values, n, L->value_dim);
+  rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -1,0 +1,359 @@
+// K3 tensor-core path: C[M,256] = epilogue( A[M,K] . B[256,K]^T ) on tcgen05 (5th-gen tensor cores), fp32-accurate
+// through 3xTF32 error compensation:   a = a_hi + a_lo, b = b_hi + b_lo (each an exact TF32 number)
+//     a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi        (dropped term a_lo.b_lo ~ 2^-22 relative)
+// Plain TF32/bf16 misses the 1e-4 parity bar of the policy loss, so every operand is stored pre-split (hi, lo) by
+// the producing kernel's epilogue and each k-step issues three kind::tf32 MMAs into the same TMEM accumulator.
+//
+// Structure (one CTA per SM, persistent over 128-row tiles, 192 threads):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B boxes) of A_hi/A_lo [128x32] and B_hi/B_lo [256x32]
+//                              per k-block into a 2-stage shared-memory ring (96 KB / stage), mbarrier full/empty.
+//   warp 1   : MMA issuer    - one elected thread, tcgen05.mma.cta_group::1.kind::tf32 M=128 N=256 K=8, accumulators
+//                              in TMEM (2 x 256 columns, double-buffered across tiles), tcgen05.commit -> mbarriers.
+//   warps 2-5: epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), bias+tanh or tanh' scaling, hi/lo split,
+//                              stores to global; overlaps the next tile's MMAs.
+// Reference op chains replaced: nn.Linear + tanh of MLPPolicy.backbone / ValueHead.mlp
+// (rlinf/models/embodiment/mlp_policy/mlp_policy.py:91-98, modules/value_head.py:37-45) and autograd's dgrad.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include "tma.cuh"
+
+namespace rb {
+namespace tc {
+
+constexpr int kStages = 2;
+constexpr int kATile = BM * BK * 4;          // 16 KB
+constexpr int kBTile = BN * BK * 4;          // 32 KB
+constexpr int kStageBytes = 2 * kATile + 2 * kBTile;  // A_hi A_lo B_hi B_lo = 96 KB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kTf32Mask = 0xffffe000u;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major; 1) | SBO>>4 [32,46) = 1024 B between 8-row groups |
+// version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10),[10,13)=2,
+// K-major A and B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// tanh(x) = sign(x) * (1 - t) / (1 + t), t = exp(-2|x|): ~1e-7 absolute error (MUFU ex2 + one IEEE division),
+// an order of magnitude fewer instructions than libdevice tanhf in the 32k-element-per-tile epilogue.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdiv_rn(1.0f - t, 1.0f + t), x);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & kTf32Mask);
+  lo = __uint_as_float(__float_as_uint(__fsub_rn(x, hi)) & kTf32Mask);
+}
+
+struct __align__(8) Barriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (p.M + BM - 1) / BM;
+  const int n_kb = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tma::mbar_init(&bars->tmem_full[b], 1);
+      tma::mbar_init(&bars->tmem_empty[b], 4);  // one arrive per epilogue warp
+    }
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      tma::prefetch_desc(&tm_a_hi);
+      tma::prefetch_desc(&tm_a_lo);
+      tma::prefetch_desc(&tm_b_hi);
+      tma::prefetch_desc(&tm_b_lo);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (int)(tile * BM);
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+          uint8_t* st = smem + s * kStageBytes;
+          tma::mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
+          tma::load_2d(st, &tm_a_hi, kb * BK, m0, &bars->full[s]);
+          tma::load_2d(st + kATile, &tm_a_lo, kb * BK, m0, &bars->full[s]);
+          tma::load_2d(st + 2 * kATile, &tm_b_hi, kb * BK, 0, &bars->full[s]);
+          tma::load_2d(st + 2 * kATile + kBTile, &tm_b_lo, kb * BK, 0, &bars->full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single thread) =================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1u;
+        const uint32_t bph = (tcount >> 1) & 1u;
+        tma::mbar_wait(&bars->tmem_empty[buf], bph ^ 1u);  // epilogue has drained this accumulator
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * BN;  // column offset
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          tma::mbar_wait(&bars->full[s], ph);
+          fence_after_sync();
+          const uint32_t sa = tma::smem_u32(smem + s * kStageBytes);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kATile);
+          const uint64_t b_hi = make_desc(sa + 2 * kATile), b_lo = make_desc(sa + 2 * kATile + kBTile);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step, in 16-byte units
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            mma_tf32(d_tmem, a_lo + koff, b_hi + koff, kIdesc, acc);   // small terms first
+            mma_tf32(d_tmem, a_hi + koff, b_lo + koff, kIdesc, 1u);
+            mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdesc, 1u);
+          }
+          mma_commit(&bars->empty[s]);  // smem stage free once these MMAs have read it
+        }
+        mma_commit(&bars->tmem_full[buf]);  // accumulator complete
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
+    uint32_t tcount = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      const uint32_t bph = (tcount >> 1) & 1u;
+      tma::mbar_wait(&bars->tmem_full[buf], bph);
+      fence_after_sync();
+      const int64_t row = tile * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* out_hi = p.c_hi + row * BN + c0;
+          if (p.epi == EPI_STORE) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(out_hi + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+            float* out_lo = p.c_lo + row * BN + c0;
+            const float* hh = p.h_hi ? p.h_hi + row * BN + c0 : nullptr;
+            const float* hl = p.h_lo ? p.h_lo + row * BN + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float v[4], hi[4], lo[4];
+              if (p.epi == EPI_BIAS_TANH_SPLIT) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+                v[0] = tanh_fast(__uint_as_float(r[j]) + b.x);
+                v[1] = tanh_fast(__uint_as_float(r[j + 1]) + b.y);
+                v[2] = tanh_fast(__uint_as_float(r[j + 2]) + b.z);
+                v[3] = tanh_fast(__uint_as_float(r[j + 3]) + b.w);
+              } else {
+                const float4 a = *reinterpret_cast<const float4*>(hh + j);
+                const float4 b = *reinterpret_cast<const float4*>(hl + j);
+                const float h0 = a.x + b.x, h1 = a.y + b.y, h2 = a.z + b.z, h3 = a.w + b.w;
+                v[0] = __uint_as_float(r[j]) * (1.0f - h0 * h0);
+                v[1] = __uint_as_float(r[j + 1]) * (1.0f - h1 * h1);
+                v[2] = __uint_as_float(r[j + 2]) * (1.0f - h2 * h2);
+                v[3] = __uint_as_float(r[j + 3]) * (1.0f - h3 * h3);
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+              *reinterpret_cast<float4*>(out_hi + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(out_lo + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(&bars->tmem_empty[buf]);
+    }
+  }
+
+  // ---- teardown ----
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// x -> (hi, lo) exact-TF32 pair; optional transpose for [R,C] -> [C,R] (weights for the dgrad GEMM)
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                    float* __restrict__ lo, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float h, l;
+    split_tf32(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                              float* __restrict__ lo, int R, int C) {
+  // out[c][r] = split(x[r][c]); small matrices (<= 256x256): simple smem-tiled transpose
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? x[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      float h, l;
+      split_tf32(tile[threadIdx.x][i], h, l);
+      hi[(size_t)c * R + r] = h;
+      lo[(size_t)c * R + r] = l;
+    }
+  }
+}
+
+int encode_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, const Params& p,
+           cudaStream_t st) {
+  if (p.K % BK != 0 || p.K <= 0 || p.M <= 0) return RB200_E_SHAPE;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
+                       reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
+                       reinterpret_cast<uintptr_t>(p.c_hi) | reinterpret_cast<uintptr_t>(p.c_lo);
+  if (al & 15) return RB200_E_ALIGN;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int e = encode_sw128(&ta_hi, a_hi, (uint64_t)p.M, (uint64_t)p.K, BM);
+  if (!e) e = encode_sw128(&ta_lo, a_lo, (uint64_t)p.M, (uint64_t)p.K, BM);
+  if (!e) e = encode_sw128(&tb_hi, b_hi, BN, (uint64_t)p.K, BN);
+  if (!e) e = encode_sw128(&tb_lo, b_lo, BN, (uint64_t)p.K, BN);
+  if (e) return RB200_E_UNSUPPORTED;
+  static bool attr_done = false;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_done = true;
+  }
+  const int64_t n_tiles = (p.M + BM - 1) / BM;
+  const int sms = rb::sm_count();
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  tc_gemm_kernel<<<grid, kThreads, kSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st) {
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)rb::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  split_kernel<<<(int)blocks, 256, 0, st>>>(x, hi, lo, n);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int split_transpose(const float* x, float* hi, float* lo, int R, int C, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  split_transpose_kernel<<<grid, block, 0, st>>>(x, hi, lo, R, C);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+}  // namespace tc
+}  // namespace rb
+
+// Debug / unit-test entry: C[M,256] (fp32) = A[M,K] . B[256,K]^T through the 3xTF32 tensor-core path.
+// `work` holds the split operands: 2*M*K + 2*256*K floats.
+extern "C" int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M, int K, float* work,
+                             rb200_stream_t stream) {
+  if (!A || !B || !C || !work) return RB200_E_NULL;
+  if (M <= 0 || K <= 0 || K % rb::tc::BK != 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  float* a_hi = work;
+  float* a_lo = a_hi + M * K;
+  float* b_hi = a_lo + M * K;
+  float* b_lo = b_hi + (int64_t)rb::tc::BN * K;
+  int e;
+  if ((e = rb::tc::split(A, a_hi, a_lo, M * K, st))) return e;
+  if ((e = rb::tc::split(B, b_hi, b_lo, (int64_t)rb::tc::BN * K, st))) return e;
+  rb::tc::Params p{};
+  p.M = M; p.K = K; p.c_hi = C; p.c_lo = C; p.epi = rb::tc::EPI_STORE;
+  return rb::tc::launch(a_hi, a_lo, b_hi, b_lo, p, st);
+}

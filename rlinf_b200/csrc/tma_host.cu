@@ -37,4 +37,21 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+
+namespace tc {
+// [rows, cols] fp32 row-major, box [box_rows x 32 floats] (128 bytes inner = one SWIZZLE_128B span)
+int encode_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 4ull};
+  cuuint32_t box[2] = {32u, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+}  // namespace tc
+
 }  // namespace rb

@@ -36,6 +36,11 @@ class MLPPolicy:
         self.flat_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._spec = self._build_spec()
         self._scratch: dict[tuple, torch.Tensor] = {}
+        # tensor-core operand cache (exact-TF32 hi/lo copies of the hidden-layer weights)
+        self.use_tensor_cores = True
+        self.wsplit = torch.zeros(int(lib.rb200_mlp_wsplit_floats(C.byref(self.layout))), dtype=torch.float32,
+                                  device=self.device)
+        self._wsplit_fresh = False
         self.reset_parameters(seed)
 
     # ---- parameter bookkeeping --------------------------------------------------------------
@@ -65,6 +70,20 @@ class MLPPolicy:
     def state_dict(self):
         return {k: v.clone() for k, v in self.named_parameters()}
 
+    def mark_params_changed(self):
+        """Call after flat_params was modified (optimiser step, load, broadcast)."""
+        self._wsplit_fresh = False
+
+    def _ws(self):
+        """Pointer to an up-to-date weight split (refreshed lazily, 20 tiny kernels), or NULL."""
+        if not self.use_tensor_cores:
+            return None
+        if not self._wsplit_fresh:
+            L.check(L.load().rb200_mlp_prepare_weights(C.byref(self.layout), L.ptr(self.flat_params),
+                                                       L.ptr(self.wsplit), L.stream_ptr()), "mlp_prepare_weights")
+            self._wsplit_fresh = True
+        return L.ptr(self.wsplit)
+
     def load_state_dict(self, sd: dict):
         views = dict(self.named_parameters())
         missing = [k for k in views if k not in sd]
@@ -72,6 +91,7 @@ class MLPPolicy:
             raise KeyError(f"missing parameters: {missing}")
         for k, v in views.items():
             v.copy_(sd[k].to(self.device, torch.float32).reshape(v.shape))
+        self.mark_params_changed()
 
     def lr_group_ends(self):
         """Flat-buffer segments by lr group, in buffer order: names containing `value_head` use
@@ -107,6 +127,7 @@ class MLPPolicy:
                 gain = 0.01 * math.sqrt(2) if name.startswith("actor_mean") else math.sqrt(2)
                 torch.nn.init.orthogonal_(w, gain=gain, generator=g)
                 p.copy_(w)
+        self.mark_params_changed()
 
     # ---- compute -------------------------------------------------------------------------------
     def _buf(self, key, numel):
@@ -121,14 +142,16 @@ class MLPPolicy:
         `idx` (int64) selecting this micro-batch's rows.  Keeps activations for `backward`."""
         lib = L.load()
         n = int(n if n is not None else (idx.numel() if idx is not None else states.shape[0]))
-        acts = self._buf("acts", lib.rb200_mlp_fwd_scratch_floats(C.byref(self.layout), n))
+        nscr = lib.rb200_mlp_fwd_scratch_floats(C.byref(self.layout), n)
+        acts = self._buf("acts", nscr)
+        work = self._buf("work", nscr)
         logp = torch.empty((n, self.act_dim), dtype=torch.float32, device=self.device)
         ent = torch.empty_like(logp) if compute_entropy else None
         vals = torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device) if (
             compute_values and self.value_dim > 0) else None
-        L.check(lib.rb200_mlp_forward(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), L.ptr(action),
-                                      L.ptr(idx), n, L.ptr(logp), L.ptr(ent), L.ptr(vals), L.ptr(acts),
-                                      L.stream_ptr()), "mlp_forward")
+        L.check(lib.rb200_mlp_forward(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states),
+                                      L.ptr(action), L.ptr(idx), n, L.ptr(logp), L.ptr(ent), L.ptr(vals), L.ptr(acts),
+                                      L.ptr(work), L.stream_ptr()), "mlp_forward")
         self._last = (states, action, idx, n, acts)
         out = {"logprobs": logp}
         if ent is not None:
@@ -142,8 +165,8 @@ class MLPPolicy:
         lib = L.load()
         states, action, idx, n, acts = self._last
         work = self._buf("work", acts.numel())
-        L.check(lib.rb200_mlp_backward(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), L.ptr(action),
-                                       L.ptr(idx), n, L.ptr(d_logprobs), L.ptr(d_entropy), L.ptr(d_values),
+        L.check(lib.rb200_mlp_backward(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states),
+                                       L.ptr(action), L.ptr(idx), n, L.ptr(d_logprobs), L.ptr(d_entropy), L.ptr(d_values),
                                        L.ptr(acts), L.ptr(work), L.ptr(self.flat_grads), L.stream_ptr()),
                 "mlp_backward")
 
@@ -153,7 +176,7 @@ class MLPPolicy:
         otherwise Philox(seed, offset) on the device."""
         lib = L.load()
         n = states.shape[0]
-        work = self._buf("sample", 6 * n * HIDDEN + 64)
+        work = self._buf("sample", lib.rb200_mlp_fwd_scratch_floats(C.byref(self.layout), n))
         if out is not None:  # write straight into rollout-buffer rows
             action, logp, vals = out
         else:
@@ -161,7 +184,7 @@ class MLPPolicy:
             logp = torch.empty_like(action)
             vals = torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device) if (
                 calculate_values and self.value_dim > 0) else None
-        L.check(lib.rb200_mlp_sample(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), L.ptr(noise),
+        L.check(lib.rb200_mlp_sample(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states), L.ptr(noise),
                                      int(seed), int(offset), L.ptr(counter), n, L.ptr(action), L.ptr(logp),
                                      L.ptr(vals), L.ptr(work), L.stream_ptr()), "mlp_sample")
         return action, logp, vals
@@ -170,9 +193,9 @@ class MLPPolicy:
         """ValueHead(states) only - bootstrap values of final observations."""
         lib = L.load()
         n = states.shape[0]
-        work = self._buf("value", 3 * n * HIDDEN + 64)
+        work = self._buf("value", lib.rb200_mlp_fwd_scratch_floats(C.byref(self.layout), n))
         vals = out if out is not None else torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device)
-        L.check(lib.rb200_mlp_value(C.byref(self.layout), L.ptr(self.flat_params), L.ptr(states), n, L.ptr(vals),
+        L.check(lib.rb200_mlp_value(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states), n, L.ptr(vals),
                                     L.ptr(work), L.stream_ptr()), "mlp_value")
         return vals
 
@@ -227,6 +250,7 @@ class FlatAdamW:
                                      L.ptr(self.exp_avg_sq), n, self._ends, lrs, len(self._kinds), self.betas[0],
                                      self.betas[1], self.eps, self.weight_decay, self.clip_grad, float(grad_scale),
                                      L.ptr(self.grad_sq), L.ptr(self.state), st), "adamw_step")
+        p.mark_params_changed()
 
     def last_grad_norm(self) -> torch.Tensor:
         """0-dim device tensor (read it on the host once per run_training, not per step)."""

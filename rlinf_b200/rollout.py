@@ -78,6 +78,7 @@ class RolloutWorker:
         buf, pol, env = self.buf, self.policy, self.env
         T, B = buf.T, buf.B
         st = L.stream_ptr()
+        pol.mark_params_changed()  # the weight split refresh is always part of the (captured) rollout
         for t in range(T):
             # policy/value inference on obs_t -> action, logprob, value rows t  (predict_action_batch)
             pol.sample(buf.states[t], noise=None if policy_noise is None else policy_noise[t], seed=self.seed,

@@ -34,10 +34,13 @@ def _synth(seed, nc, B, C, p_done=0.05):
 
 
 def rank_consistent(ours: torch.Tensor, ref: torch.Tensor):
-    """Ranks agree up to ties: sorting by our values orders the reference values, and vice versa."""
-    o, r = ours.flatten().cpu(), ref.flatten().cpu()
-    assert bool((r[torch.argsort(o, stable=True)].diff() >= 0).all())
-    assert bool((o[torch.argsort(r, stable=True)].diff() >= 0).all())
+    """Ranks agree up to ties: ours_i < ours_j implies ref_i <= ref_j, and vice versa. (Both are monotone maps
+    of the same bit-exact raw advantages; a 1-ulp difference in mean/std may merge or split ties but never swaps.)"""
+    o, r = ours.flatten().cpu().double().numpy(), ref.flatten().cpu().double().numpy()
+    order = np.lexsort((r, o))  # primary key o, ties ordered by r
+    assert (np.diff(r[order]) >= 0).all()
+    order = np.lexsort((o, r))
+    assert (np.diff(o[order]) >= 0).all()
 
 
 # ---------------------------------------------------------------------------------------------

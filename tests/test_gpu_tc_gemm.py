@@ -1,0 +1,28 @@
+"""tcgen05 3xTF32 GEMM building block vs an fp64 matmul (GPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K", [(128, 32), (128, 256), (1000, 128), (5000, 256), (262144, 256)])
+def test_tc_gemm_matches_fp64(M, K):
+    from rlinf_b200 import _lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(256, K, device="cuda", generator=g) / K ** 0.5
+    C = torch.empty(M, 256, device="cuda")
+    work = torch.empty(2 * M * K + 512 * K, device="cuda")
+    L.check(lib.rb200_tc_gemm(L.ptr(A), L.ptr(B), L.ptr(C), M, K, L.ptr(work), L.stream_ptr()), "tc_gemm")
+    torch.cuda.synchronize()
+    n = min(M, 4096)
+    ref = (A[:n].double() @ B.double().T)
+    err = (C[:n].double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp32-level accuracy (plain TF32 would be ~1e-3 relative)
+    assert err <= 5e-6 * scale + 1e-6, (err, scale)
+    if M > n:  # spot-check the tail rows too
+        ref2 = (A[-256:].double() @ B.double().T)
+        assert (C[-256:].double() - ref2).abs().max().item() <= 5e-6 * scale + 1e-6
