@@ -259,6 +259,11 @@ int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float
 int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M, int K, float* work,
                   rb200_stream_t stream);
 
+/* Weight-gradient counterpart (unit-test entry): dW[256,IN] += Z[n,256]^T . H[n,IN], IN % 32 == 0, IN <= 256;
+ * `work` = 2*n*(256+IN) floats. */
+int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN, float* work,
+                   rb200_stream_t stream);
+
 /* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
  * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */
 int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,

@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import dist_utils as D
 from . import ops
 from .algorithms import calculate_adv_and_returns
 from .config import wrap
@@ -134,7 +135,7 @@ class EmbodiedActor:
         key = (n, self.cfg.actor.seed + self._rank)
         if key not in self._perm_cache:
             g = torch.Generator()
-            g.manual_seed(key[1])
+            g.manual_seed(D.shuffle_seed(self.cfg.actor.seed, self._rank))
             self._perm_cache[key] = torch.randperm(n, generator=g).to(self.device)
         return self._perm_cache[key]
 
@@ -145,13 +146,10 @@ class EmbodiedActor:
         shuffle_id = self._shuffle_id(rollout_size)
         batch = process_nested_dict_for_train(rb, shuffle_id)
         self.rollout_batch = batch
-        batch_size_per_rank = cfg.actor.global_batch_size // self._world_size
-        assert rollout_size % batch_size_per_rank == 0, f"{rollout_size} is not divisible by {batch_size_per_rank}"
         mbs = cfg.actor.micro_batch_size
-        assert batch_size_per_rank % mbs == 0, f"train_global_batch_size={batch_size_per_rank}, {mbs}"
-        self.gradient_accumulation = batch_size_per_rank // mbs
+        batch_size_per_rank, self.gradient_accumulation, n_global = D.per_rank_batch(
+            cfg.actor.global_batch_size, self._world_size, mbs, rollout_size)
         update_epoch = cfg.algorithm.get("update_epoch", 1)
-        n_global = rollout_size // batch_size_per_rank
         n_steps = update_epoch * n_global
         n_micro = n_steps * self.gradient_accumulation
         metric_rows = torch.zeros(n_micro, L.NUM_METRICS, dtype=torch.float32, device=self.device)
@@ -206,9 +204,8 @@ class EmbodiedActor:
         """all-reduce(SUM) of the flat gradient buffer over the data-parallel ranks, then one fused
         norm / clip / AdamW pass that also applies the 1/world_size average."""
         self.optimizer_steps += 1
-        if self._world_size > 1:
-            dist.all_reduce(self.model.flat_grads, op=dist.ReduceOp.SUM, group=self.pg)
-        self.optimizer.step(grad_scale=1.0 / self._world_size)
+        scale = D.allreduce_flat_grads(self.model.flat_grads, self._world_size, self.pg)
+        self.optimizer.step(grad_scale=scale)
         return self.optimizer.state.clone(), self.optimizer.lr_list()
 
     def _reduce_metrics(self, metric_rows, step_rows, lr_rows) -> dict:
@@ -218,14 +215,7 @@ class EmbodiedActor:
         mean_vec = metric_rows.mean(dim=0)
         ev_sum = metric_rows[:, 10:15].sum(dim=0)
         grad_norm = step_rows[:, 1].mean().to(torch.float32)
-        packed = torch.cat([mean_vec, ev_sum, grad_norm.reshape(1)])
-        if self._world_size > 1:
-            avg_part = packed.clone()
-            dist.all_reduce(avg_part, op=dist.ReduceOp.SUM, group=self.pg)
-            avg_part /= self._world_size
-            ev_tot = ev_sum.clone()
-            dist.all_reduce(ev_tot, op=dist.ReduceOp.SUM, group=self.pg)
-            packed = torch.cat([avg_part[: L.NUM_METRICS], ev_tot, avg_part[-1:]])
+        packed = D.reduce_metric_pack(mean_vec, ev_sum, grad_norm, self._world_size, self.pg)
         host = packed.tolist()
         out = {}
         slots = L.ACTOR_SLOTS + ((8, 9) if with_critic else ()) + (15, 16)
@@ -254,6 +244,6 @@ class EmbodiedActor:
         separate replica buffer gets a device copy; across ranks one NCCL broadcast of the flat buffer."""
         if rollout_params is not None and rollout_params.data_ptr() != self.model.flat_params.data_ptr():
             rollout_params.copy_(self.model.flat_params)
-        if self._world_size > 1 and self.cfg.runner.get("broadcast_params", True):
-            dist.broadcast(self.model.flat_params, src=src, group=self.pg)
+        if self.cfg.runner.get("broadcast_params", True):
+            D.broadcast_params(self.model.flat_params, self._world_size, src, self.pg)
         self.model.mark_params_changed()

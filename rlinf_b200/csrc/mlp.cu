@@ -50,7 +50,7 @@ constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
 
 __device__ __forceinline__ void split1(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = __uint_as_float(__float_as_uint(__fsub_rn(x, hi)) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & 0xffffe000u);  // round-to-nearest TF32
 }
 __device__ __forceinline__ void store_split(float* hi, float* lo, int64_t off, float4 v) {
   float4 h, l;
@@ -388,8 +388,9 @@ int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, con
 }
 
 // backward through the three hidden layers of one tower, given dZ3 (hi,lo). tmpA/tmpB: [2][n,256] scratch.
-int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
-                   const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB, float* g_w0,
+int tower_backward(const float* X, const float* xsplit, const int64_t* idx, int64_t n, int in_dim, const TowerW& w,
+                   const TowerWS* ws, const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB,
+                   float* g_w0,
                    float* g_b0, float* g_w1, float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
   const int64_t rows_per_split = 4096;
   const int splits = (int)((n + rows_per_split - 1) / rows_per_split);
@@ -399,7 +400,17 @@ int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, co
   int e;
   auto wgrad = [&](const float* dZ, const float* Hin, const float* Hin_lo, const int64_t* in_rows, int in_ld,
                    float* gw, float* gb) -> int {
-    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]      (fp32 SIMT, split over samples, atomics)
+    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
+    const int64_t cs_rows_ = cs_rows;
+    if (ws && Hin_lo && !in_rows && (in_ld % rb::tc::BK == 0) && in_ld <= 256) {  // tensor cores (3xTF32)
+      int ee = rb::tc::wgrad(dZ, dZ + L, Hin, Hin_lo, gw, n, in_ld, st);
+      if (ee) return ee;
+      colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows_);
+      rb::count_launch();
+      cudaError_t ce = cudaPeekAtLastError();
+      return ce == cudaSuccess ? 0 : (int)ce;
+    }
+    // fp32 SIMT, split over samples, atomics
     GemmArgs g{};
     g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = Hin; g.B2 = Hin_lo; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw;
     g.ldc = in_ld; g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
@@ -430,6 +441,8 @@ int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, co
   if ((e = dgrad(dZ3, w.w2, ws ? ws->w2th : nullptr, ws ? ws->w2tl : nullptr, H2, tmpA))) return e;  // dZ2
   if ((e = wgrad(tmpA, H1, H1 + L, nullptr, kH, g_w1, g_b1))) return e;
   if ((e = dgrad(tmpA, w.w1, ws ? ws->w1th : nullptr, ws ? ws->w1tl : nullptr, H1, tmpB))) return e;  // dZ1
+  if (ws && xsplit && !idx && in_dim % rb::tc::BK == 0)  // forward left the exact-TF32 split of X in `work`
+    return wgrad(tmpB, xsplit, xsplit + n * in_dim, nullptr, in_dim, g_w0, g_b0);
   return wgrad(tmpB, X, nullptr, idx, in_dim, g_w0, g_b0);
 }
 
@@ -600,11 +613,13 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   }
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, dZ3, tA,
-                          tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
+  const float* xsplit = work + 6 * PF;  // written by rb200_mlp_forward (same `work` buffer), untouched since
+  if ((e = tower_backward(states, xsplit, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, dZ3,
+                          tA, tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
     return e;
   if (d_values &&
-      (e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, dY3, uA, uB,
+      (e = tower_backward(states, xsplit, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, dY3, uA,
+                          uB,
                           G + L->vw0, G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
     return e;
   return RB200_OK;

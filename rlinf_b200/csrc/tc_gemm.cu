@@ -89,7 +89,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & kTf32Mask);
-  lo = __uint_as_float(__float_as_uint(__fsub_rn(x, hi)) & kTf32Mask);
+  lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & kTf32Mask);  // round-to-nearest TF32 (no bias)
 }
 
 struct __align__(8) Barriers {
@@ -98,6 +98,8 @@ struct __align__(8) Barriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias[BN];  // epilogue reads the bias through shared memory (broadcast LDS) instead of 64 dependent LDGs / tile
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
+  if (p.epi == EPI_BIAS_TANH_SPLIT)
+    for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = p.bias[i];
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -201,7 +205,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(taddr0 + c0, r);
+        tmem_ld32(taddr0 + c0, r);  // asynchronous until tmem_ld_wait
+        // dgrad: fetch this row's 32 previous-activation values (hi + lo) while the TMEM load is in flight
+        float4 hv[8];
+        if (p.epi == EPI_TANHGRAD_SPLIT && row_ok) {
+          const float4* hh = reinterpret_cast<const float4*>(p.h_hi + row * BN + c0);
+          const float4* hl = reinterpret_cast<const float4*>(p.h_lo + row * BN + c0);
+          float4 a[8], b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = __ldg(hh + j);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = __ldg(hl + j);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hv[j] = make_float4(a[j].x + b[j].x, a[j].y + b[j].y, a[j].z + b[j].z, a[j].w + b[j].w);
+        }
         tmem_ld_wait();
         if (row_ok) {
           float* out_hi = p.c_hi + row * BN + c0;
@@ -212,25 +229,21 @@ __global__ void __launch_bounds__(kThreads, 1)
                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           } else {
             float* out_lo = p.c_lo + row * BN + c0;
-            const float* hh = p.h_hi ? p.h_hi + row * BN + c0 : nullptr;
-            const float* hl = p.h_lo ? p.h_lo + row * BN + c0 : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float v[4], hi[4], lo[4];
               if (p.epi == EPI_BIAS_TANH_SPLIT) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+                const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j]);
                 v[0] = tanh_fast(__uint_as_float(r[j]) + b.x);
                 v[1] = tanh_fast(__uint_as_float(r[j + 1]) + b.y);
                 v[2] = tanh_fast(__uint_as_float(r[j + 2]) + b.z);
                 v[3] = tanh_fast(__uint_as_float(r[j + 3]) + b.w);
               } else {
-                const float4 a = *reinterpret_cast<const float4*>(hh + j);
-                const float4 b = *reinterpret_cast<const float4*>(hl + j);
-                const float h0 = a.x + b.x, h1 = a.y + b.y, h2 = a.z + b.z, h3 = a.w + b.w;
-                v[0] = __uint_as_float(r[j]) * (1.0f - h0 * h0);
-                v[1] = __uint_as_float(r[j + 1]) * (1.0f - h1 * h1);
-                v[2] = __uint_as_float(r[j + 2]) * (1.0f - h2 * h2);
-                v[3] = __uint_as_float(r[j + 3]) * (1.0f - h3 * h3);
+                const float4 h = hv[j >> 2];
+                v[0] = __uint_as_float(r[j]) * (1.0f - h.x * h.x);
+                v[1] = __uint_as_float(r[j + 1]) * (1.0f - h.y * h.y);
+                v[2] = __uint_as_float(r[j + 2]) * (1.0f - h.z * h.z);
+                v[3] = __uint_as_float(r[j + 3]) * (1.0f - h.w * h.w);
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
@@ -252,6 +265,136 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM on the tensor cores:  dW[256, IN] += sum_m dZ[m, :]^T . H[m, :]      (IN = 32..256, % 32)
+// Both operands are "MN-major" for the MMA (the reduction index m = sample is the strided dimension):
+//   A(out, m) = dZ[m][out],  B(in, m) = H[m][in].
+// Shared-memory tile of one operand for a k-block of 32 samples: G groups of [32 samples][32 floats] (TMA box
+// {32 floats, 32 rows}, SWIZZLE_128B_ATOM_32B) = the canonical MN-major layout for 32-bit operands
+// (UMMA LayoutType::SWIZZLE_128B_BASE32B: atoms of 4 samples x 128 B, Swizzle<2,5,2>) with LBO = 4096 B between
+// 32-column groups and SBO = 512 B between 4-sample atoms; one K=8 MMA step consumes two atoms (1024 B) per group.
+// Grid = 2 output tiles (128 rows of dW each) x C sample chunks; each CTA accumulates its chunk in TMEM and adds the
+// tile to dW with vector atomics.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_z_hi, const __grid_constant__ CUtensorMap tm_z_lo,
+                    const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
+                    float* __restrict__ dW, int64_t n, int IN, int kb_per_chunk) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int out_tile = blockIdx.x & 1, chunk = blockIdx.x >> 1;
+  const int n_kb_total = (int)((n + BK - 1) / BK);
+  const int kb0 = chunk * kb_per_chunk;
+  const int kb1 = (kb0 + kb_per_chunk < n_kb_total) ? kb0 + kb_per_chunk : n_kb_total;
+  const int n_kb = kb1 - kb0;  // may be <= 0 for trailing chunks
+  const int gB = IN / 32;      // 32-column groups of the B operand
+  const uint32_t b_bytes = (uint32_t)IN * BK * 4;
+  const uint32_t tmem_cols = IN <= 128 ? 128u : 256u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->empty[s], 1);
+    }
+    tma::mbar_init(&bars->tmem_full[0], 1);
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (n_kb > 0) {
+    if (warp == 0) {
+      // ---- TMA producer: lane 0 arms the barrier, lanes 0..(2*4+2*gB-1) each issue one 4 KB box ----
+      const int n_box = 8 + 2 * gB;
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        if (lane == 0) {
+          tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+          tma::mbar_arrive_expect_tx(&bars->full[s], 2 * kATile + 2 * b_bytes);
+        }
+        __syncwarp();
+        if (lane < n_box) {
+          uint8_t* st = smem + s * kStageBytes;
+          const int m0 = (kb0 + it) * BK;
+          if (lane < 8) {  // A: dZ hi (boxes 0-3), lo (4-7); 32-column group g of this CTA's 128 output rows
+            const int g = lane & 3;
+            tma::load_2d(st + (lane < 4 ? 0 : kATile) + g * 4096, lane < 4 ? &tm_z_hi : &tm_z_lo,
+                         out_tile * 128 + g * 32, m0, &bars->full[s]);
+          } else {         // B: H hi then lo
+            const int j = lane - 8;
+            const bool lo = j >= gB;
+            const int g = lo ? j - gB : j;
+            tma::load_2d(st + 2 * kATile + (lo ? b_bytes : 0) + g * 4096, lo ? &tm_h_lo : &tm_h_hi, g * 32, m0,
+                         &bars->full[s]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(IN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int it = 0; it < n_kb; ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          tma::mbar_wait(&bars->full[s], ph);
+          fence_after_sync();
+          const uint32_t sa = tma::smem_u32(smem + s * kStageBytes);
+          const uint64_t a_hi = make_desc_mn(sa), a_lo = make_desc_mn(sa + kATile);
+          const uint64_t b_hi = make_desc_mn(sa + 2 * kATile), b_lo = make_desc_mn(sa + 2 * kATile + b_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t koff = (uint64_t)((k * 1024) >> 4);  // next 8 samples (two 4-sample atoms)
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            mma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, acc);
+            mma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+            mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+          }
+          mma_commit(&bars->empty[s]);
+        }
+        mma_commit(&bars->tmem_full[0]);
+      }
+    } else {
+      const int q = warp & 3;
+      tma::mbar_wait(&bars->tmem_full[0], 0);
+      fence_after_sync();
+      const int row = out_tile * 128 + q * 32 + lane;  // output row of dW (always < 256)
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < IN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        tmem_ld_wait();
+        float* dst = dW + (size_t)row * IN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + j),
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3])));
+      }
+      fence_before_sync();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -303,7 +446,7 @@ int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float*
   if (!e) e = encode_sw128(&tb_lo, b_lo, BN, (uint64_t)p.K, BN);
   if (e) return RB200_E_UNSUPPORTED;
   static bool attr_done = false;
-  constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + BN * 4;
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
@@ -313,6 +456,39 @@ int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float*
   const int sms = rb::sm_count();
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   tc_gemm_kernel<<<grid, kThreads, kSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int encode_sw128_box32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols);
+
+int wgrad(const float* z_hi, const float* z_lo, const float* h_hi, const float* h_lo, float* dW, int64_t n, int IN,
+          cudaStream_t st) {
+  if (n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(z_hi) | reinterpret_cast<uintptr_t>(z_lo) |
+                       reinterpret_cast<uintptr_t>(h_hi) | reinterpret_cast<uintptr_t>(h_lo) |
+                       reinterpret_cast<uintptr_t>(dW);
+  if (al & 15) return RB200_E_ALIGN;
+  CUtensorMap tz_hi, tz_lo, th_hi, th_lo;
+  int e = encode_sw128_box32(&tz_hi, z_hi, (uint64_t)n, 256);
+  if (!e) e = encode_sw128_box32(&tz_lo, z_lo, (uint64_t)n, 256);
+  if (!e) e = encode_sw128_box32(&th_hi, h_hi, (uint64_t)n, (uint64_t)IN);
+  if (!e) e = encode_sw128_box32(&th_lo, h_lo, (uint64_t)n, (uint64_t)IN);
+  if (e) return RB200_E_UNSUPPORTED;
+  static bool attr_done = false;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + BN * 4;
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_done = true;
+  }
+  const int n_kb = (int)((n + BK - 1) / BK);
+  int chunks = rb::sm_count() / 2;
+  if (chunks < 1) chunks = 1;
+  if (chunks > n_kb) chunks = n_kb;
+  const int kb_per_chunk = (n_kb + chunks - 1) / chunks;
+  tc_wgrad_kernel<<<2 * chunks, kThreads, kSmem, st>>>(tz_hi, tz_lo, th_hi, th_lo, dW, n, IN, kb_per_chunk);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
@@ -356,4 +532,20 @@ extern "C" int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M
   rb::tc::Params p{};
   p.M = M; p.K = K; p.c_hi = C; p.c_lo = C; p.epi = rb::tc::EPI_STORE;
   return rb::tc::launch(a_hi, a_lo, b_hi, b_lo, p, st);
+}
+
+// Unit-test entry for the weight-gradient GEMM: dW[256, IN] += Z[n,256]^T . H[n,IN]; work = 2*n*(256+IN) floats.
+extern "C" int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN, float* work,
+                              rb200_stream_t stream) {
+  if (!Z || !H || !dW || !work) return RB200_E_NULL;
+  if (n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  float* z_hi = work;
+  float* z_lo = z_hi + n * 256;
+  float* h_hi = z_lo + n * 256;
+  float* h_lo = h_hi + n * IN;
+  int e;
+  if ((e = rb::tc::split(Z, z_hi, z_lo, n * 256, st))) return e;
+  if ((e = rb::tc::split(H, h_hi, h_lo, n * IN, st))) return e;
+  return rb::tc::wgrad(z_hi, z_lo, h_hi, h_lo, dW, n, IN, st);
 }

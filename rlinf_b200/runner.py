@@ -26,10 +26,9 @@ class EmbodiedRunner:
         self.rank = rank if rank is not None else (dist.get_rank() if self._dist else 0)
         self.world_size = world_size if world_size is not None else (dist.get_world_size() if self._dist else 1)
         et, m = cfg.env.train, cfg.actor.model
-        assert et.total_num_envs % self.world_size == 0
-        self.B = et.total_num_envs // self.world_size  # envs per rank
-        gs = cfg.algorithm.get("group_size", 1)
-        assert self.B % gs == 0, "envs per rank must be a multiple of group_size (config.py:1109-1117)"
+        from .dist_utils import shard_envs
+        self.env_start, self.B = shard_envs(et.total_num_envs, self.world_size, self.rank,
+                                            cfg.algorithm.get("group_size", 1))  # envs owned by this rank
         self.T = et.max_steps_per_rollout_epoch
         self.actor = EmbodiedActor(cfg, rank=self.rank, world_size=self.world_size, process_group=process_group)
         pol = self.actor.model

@@ -26,3 +26,22 @@ def test_tc_gemm_matches_fp64(M, K):
     if M > n:  # spot-check the tail rows too
         ref2 = (A[-256:].double() @ B.double().T)
         assert (C[-256:].double() - ref2).abs().max().item() <= 5e-6 * scale + 1e-6
+
+
+@pytest.mark.parametrize("n,IN", [(32, 32), (1000, 128), (4096, 256), (70000, 256), (262144, 128)])
+def test_tc_wgrad_matches_fp64(n, IN):
+    from rlinf_b200 import _lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(n + IN)
+    Z = torch.randn(n, 256, device="cuda", generator=g) / n ** 0.5
+    H = torch.randn(n, IN, device="cuda", generator=g)
+    dW = torch.ones(256, IN, device="cuda")  # accumulates (+=)
+    work = torch.empty(2 * n * (256 + IN), device="cuda")
+    L.check(lib.rb200_tc_wgrad(L.ptr(Z), L.ptr(H), L.ptr(dW), n, IN, L.ptr(work), L.stream_ptr()), "tc_wgrad")
+    torch.cuda.synchronize()
+    ref = 1.0 + Z.double().T @ H.double()
+    err = (dW.double() - ref).abs().max().item()
+    scale = (ref - 1.0).abs().max().item()
+    # fp32 accumulation over n samples (TMEM accumulators are fp32, like any fp32 GEMM): error grows ~sqrt(n)
+    assert err <= (5e-6 + 2e-7 * n ** 0.5) * scale + 2e-6, (err, scale)
