@@ -85,20 +85,39 @@ __device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-pipelined kernel. CTA = 2 warps: warp 0 consumes (32 trajectories), warp 1 lane 0 produces.
+// TMA-pipelined, warp-specialised kernel. One CTA per 32 trajectories, 6 warps:
+//   warp 0      producer : one thread streams [16 steps x 32 traj] tiles (rewards, values(+1 row), dones, mask) with TMA
+//   warps 1,2   delta    : delta_t and the recurrence coefficient c_t = (gamma*lambda)*!done  (no dependence on g)
+//   warp 3      chain    : g_t = delta_t + c_t * g_{t+1}, strictly sequential, 2 dependent fp32 ops per step
+//   warps 4,5   epilogue : ret = g + V, adv = ret - V, coalesced 128-byte stores, statistics
+// A single warp doing all of this is issue-bound (ncu round-1 v1: 46 us, ~107 cycles / step); splitting the work
+// that does not depend on the carry across warps leaves ~9 cycles / step on the sequential warp.
+// Stage hand-off: full (TMA) -> dready (delta warps) -> gready (chain) -> empty (epilogue), all mbarriers.
 // Requires B % 16 == 0 (16-byte global strides for the byte tensors) and 16-byte aligned bases.
 // ---------------------------------------------------------------------------------------------
+constexpr int kStagesWS = 8;
+struct __align__(128) StageWS {
+  float r[kR][kW];
+  float v[kR + 1][kW];     // rows t0 .. t0+16 (the extra row is V[t+1] of the tile's last step)
+  uint8_t d[kR][kW];       // done AFTER step t (rows t0+1 .. t0+16 of dones)
+  uint8_t m[kR][kW];
+  float2 dc[kR][kW];       // {delta_t, c_t}
+  float g[kR][kW];
+};
+constexpr uint32_t kWsThreads = 192;
+
 template <bool HAS_V, bool HAS_MASK, bool HAS_STATS>
-__global__ void __launch_bounds__(64) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r,
-                                                     const __grid_constant__ CUtensorMap tm_v,
-                                                     const __grid_constant__ CUtensorMap tm_d,
-                                                     const __grid_constant__ CUtensorMap tm_m,
-                                                     const float* __restrict__ values, float* __restrict__ adv,
-                                                     float* __restrict__ ret, double* __restrict__ stats, int T,
-                                                     int B, float gamma, float coef) {
-  __shared__ Stage stages[kS];
-  __shared__ __align__(8) uint64_t full_bar[kS];
-  __shared__ __align__(8) uint64_t empty_bar[kS];
+__global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r,
+                                                             const __grid_constant__ CUtensorMap tm_v,
+                                                             const __grid_constant__ CUtensorMap tm_d,
+                                                             const __grid_constant__ CUtensorMap tm_m,
+                                                             float* __restrict__ adv, float* __restrict__ ret,
+                                                             double* __restrict__ stats, int T, int B, float gamma,
+                                                             float coef) {
+  extern __shared__ uint8_t smem_raw[];
+  StageWS* stages = reinterpret_cast<StageWS*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[kStagesWS], dready_bar[kStagesWS], gready_bar[kStagesWS],
+      empty_bar[kStagesWS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * kW;
@@ -106,89 +125,127 @@ __global__ void __launch_bounds__(64) gae_tma_kernel(const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kS; ++s) {
+    for (int s = 0; s < kStagesWS; ++s) {
       rb::tma::mbar_init(&full_bar[s], 1);
-      rb::tma::mbar_init(&empty_bar[s], 1);
+      rb::tma::mbar_init(&dready_bar[s], 2);
+      rb::tma::mbar_init(&gready_bar[s], 1);
+      rb::tma::mbar_init(&empty_bar[s], 2);
     }
     rb::tma::fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == 1) {
+  if (warp == 0) {
     if (lane == 0) {
       rb::tma::prefetch_desc(&tm_r);
       rb::tma::prefetch_desc(&tm_d);
       if (HAS_V) rb::tma::prefetch_desc(&tm_v);
       if (HAS_MASK) rb::tma::prefetch_desc(&tm_m);
-      constexpr uint32_t kBytes = sizeof(float) * kR * kW + (HAS_V ? sizeof(float) * kR * kW : 0) + kR * kW +
+      constexpr uint32_t kBytes = sizeof(float) * kR * kW + (HAS_V ? sizeof(float) * (kR + 1) * kW : 0) + kR * kW +
                                   (HAS_MASK ? kR * kW : 0);
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kS;
-        const uint32_t ph = (uint32_t)(it / kS) & 1u;
+        const int s = it % kStagesWS;
+        const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
         rb::tma::mbar_wait(&empty_bar[s], ph ^ 1u);
         const int t0 = T - (it + 1) * kR;  // may be negative on the last tile: OOB rows are zero-filled
         rb::tma::mbar_arrive_expect_tx(&full_bar[s], kBytes);
         rb::tma::load_2d(&stages[s].r[0][0], &tm_r, col0, t0, &full_bar[s]);
         if (HAS_V) rb::tma::load_2d(&stages[s].v[0][0], &tm_v, col0, t0, &full_bar[s]);
-        rb::tma::load_2d(&stages[s].d[0][0], &tm_d, col0, t0 + 1, &full_bar[s]);  // done AFTER step t
+        rb::tma::load_2d(&stages[s].d[0][0], &tm_d, col0, t0 + 1, &full_bar[s]);
         if (HAS_MASK) rb::tma::load_2d(&stages[s].m[0][0], &tm_m, col0, t0, &full_bar[s]);
       }
     }
-    return;
-  }
-
-  // ---- consumer warp ----
-  const int col = col0 + lane;
-  const bool in_range = col < B;
-  float v_next = (HAS_V && in_range) ? values[(size_t)T * B + col] : 0.0f;  // bootstrap row V[T]
-  float g = 0.0f;
-  Acc acc_a, acc_r;
-  // Full tiles are processed branch-free (so ptxas hoists the tile's shared-memory loads above the dependent
-  // fp32 chain); only a ragged first-in-time tile (T % kR != 0) takes the guarded path.
-  auto consume = [&](const Stage& st, int t0, auto full_tag) {
-    constexpr bool FULL = decltype(full_tag)::value;
+  } else if (warp <= 2) {
+    // ---- delta warps: rows rr = w, w+2, ... of every tile ----
+    const int w = warp - 1;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kStagesWS;
+      const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
+      rb::tma::mbar_wait(&full_bar[s], ph);
+      StageWS& st = stages[s];
 #pragma unroll
-    for (int rr = kR - 1; rr >= 0; --rr) {
-      const int t = t0 + rr;
-      if (FULL || t >= 0) {  // warp-uniform; compiled out for full tiles
-        const float r = st.r[rr][lane];
-        const float vt = HAS_V ? st.v[rr][lane] : 0.0f;
-        const uint8_t dn = st.d[rr][lane];
+      for (int k = 0; k < kR / 2; ++k) {
+        const int rr = 2 * k + w;
+        const float nd = st.d[rr][lane] ? 0.0f : 1.0f;
+        float delta;
+        if (HAS_V) {
+          const float boot = __fmul_rn(__fmul_rn(gamma, st.v[rr + 1][lane]), nd);
+          delta = __fsub_rn(__fadd_rn(st.r[rr][lane], boot), st.v[rr][lane]);
+        } else {
+          delta = st.r[rr][lane];
+        }
+        st.dc[rr][lane] = make_float2(delta, __fmul_rn(coef, nd));
+      }
+      __syncwarp();
+      if (lane == 0) rb::tma::mbar_arrive(&dready_bar[s]);
+    }
+  } else if (warp == 3) {
+    // ---- chain warp: the only sequential part ----
+    float g = 0.0f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kStagesWS;
+      const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
+      rb::tma::mbar_wait(&dready_bar[s], ph);
+      StageWS& st = stages[s];
+      float2 dc[kR];
+#pragma unroll
+      for (int rr = 0; rr < kR; ++rr) dc[rr] = st.dc[rr][lane];
+#pragma unroll
+      for (int rr = kR - 1; rr >= 0; --rr) {
+        g = __fadd_rn(dc[rr].x, __fmul_rn(dc[rr].y, g));
+        st.g[rr][lane] = g;
+      }
+      __syncwarp();
+      if (lane == 0) rb::tma::mbar_arrive(&gready_bar[s]);
+    }
+  } else {
+    // ---- epilogue warps ----
+    const int w = warp - 4;
+    const int col = col0 + lane;
+    const bool in_range = col < B;
+    Acc acc_a, acc_r;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kStagesWS;
+      const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
+      const int t0 = T - (it + 1) * kR;
+      rb::tma::mbar_wait(&gready_bar[s], ph);
+      const StageWS& st = stages[s];
+#pragma unroll
+      for (int k = 0; k < kR / 2; ++k) {
+        const int rr = 2 * k + w;
+        const int t = t0 + rr;
+        const float g = st.g[rr][lane];
         float rt, ad;
-        gae_step<HAS_V>(r, vt, v_next, dn, gamma, coef, g, rt, ad);
-        v_next = vt;
-        if (in_range) {
+        if (HAS_V) {
+          const float vt = st.v[rr][lane];
+          rt = __fadd_rn(g, vt);
+          ad = __fsub_rn(rt, vt);
+        } else {
+          rt = g;
+          ad = g;
+        }
+        if (in_range && t >= 0) {
           const size_t o = (size_t)t * B + col;
           adv[o] = ad;
           ret[o] = rt;
-        }
-        if (HAS_STATS) {
-          const bool valid = in_range && (HAS_MASK ? (st.m[rr][lane] != 0) : true);
-          if (valid) {
-            acc_a.add(ad);
-            acc_r.add(rt);
+          if (HAS_STATS) {
+            const bool valid = HAS_MASK ? (st.m[rr][lane] != 0) : true;
+            if (valid) {
+              acc_a.add(ad);
+              acc_r.add(rt);
+            }
           }
         }
       }
+      if (HAS_STATS) {
+        acc_a.fold();
+        acc_r.fold();
+      }
+      __syncwarp();
+      if (lane == 0) rb::tma::mbar_arrive(&empty_bar[s]);
     }
-    if (HAS_STATS) {
-      acc_a.fold();
-      acc_r.fold();
-    }
-  };
-  for (int it = 0; it < n_iter; ++it) {
-    const int s = it % kS;
-    const uint32_t ph = (uint32_t)(it / kS) & 1u;
-    const int t0 = T - (it + 1) * kR;
-    rb::tma::mbar_wait(&full_bar[s], ph);
-    if (t0 >= 0)
-      consume(stages[s], t0, std::true_type{});
-    else
-      consume(stages[s], t0, std::false_type{});
-    __syncwarp();
-    if (lane == 0) rb::tma::mbar_arrive(&empty_bar[s]);
+    if (HAS_STATS) flush_stats(acc_a, acc_r, stats);
   }
-  if (HAS_STATS) flush_stats(acc_a, acc_r, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,14 +339,23 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
   if (aligned) {
     CUtensorMap tm_r, tm_v, tm_d, tm_m;
     int e = rb::encode_tmap_2d(&tm_r, rewards, 4, (uint64_t)T, (uint64_t)B, kR, kW);
-    if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kR, kW);
+    if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kR + 1, kW);
     if (!e) e = rb::encode_tmap_2d(&tm_d, dones, 1, (uint64_t)T + 1, (uint64_t)B, kR, kW);
     if (!e && HAS_MASK) e = rb::encode_tmap_2d(&tm_m, mask, 1, (uint64_t)T, (uint64_t)B, kR, kW);
     if (!HAS_V) tm_v = tm_r;
     if (!HAS_MASK) tm_m = tm_d;
     if (!e) {
+      constexpr int kSmem = kStagesWS * (int)sizeof(StageWS) + 128;
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaError_t ce = cudaFuncSetAttribute(gae_tma_kernel<HAS_V, HAS_MASK, HAS_STATS>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_done = true;
+      }
       gae_tma_kernel<HAS_V, HAS_MASK, HAS_STATS>
-          <<<grid, 64, 0, st>>>(tm_r, tm_v, tm_d, tm_m, values, adv, ret, stats, T, B, gamma, coef); rb::count_launch();
+          <<<grid, kWsThreads, kSmem, st>>>(tm_r, tm_v, tm_d, tm_m, adv, ret, stats, T, B, gamma, coef);
+      rb::count_launch();
       RB_RETURN_LAUNCH();
     }
     // descriptor encode failed (e.g. driver entry point unavailable): use the generic kernel

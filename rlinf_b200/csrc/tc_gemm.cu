@@ -10,7 +10,8 @@
 //   warp 1   : MMA issuer    - one elected thread, tcgen05.mma.cta_group::1.kind::tf32 M=128 N=256 K=8, accumulators
 //                              in TMEM (2 x 256 columns, double-buffered across tiles), tcgen05.commit -> mbarriers.
 //   warps 2-5: epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), bias+tanh or tanh' scaling, hi/lo split,
-//                              stores to global; overlaps the next tile's MMAs.
+//                              transposed through a swizzled shared-memory block so that every global store / load
+//                              instruction covers complete 128-byte row segments; overlaps the next tile's MMAs.
 // Reference op chains replaced: nn.Linear + tanh of MLPPolicy.backbone / ValueHead.mlp
 // (rlinf/models/embodiment/mlp_policy/mlp_policy.py:91-98, modules/value_head.py:37-45) and autograd's dgrad.
 #include "common.cuh"
@@ -24,7 +25,7 @@ constexpr int kStages = 2;
 constexpr int kATile = BM * BK * 4;          // 16 KB
 constexpr int kBTile = BN * BK * 4;          // 32 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kBTile;  // A_hi A_lo B_hi B_lo = 96 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTf32Mask = 0xffffe000u;
 
@@ -80,11 +81,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // K-major A and B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-// tanh(x) = sign(x) * (1 - t) / (1 + t), t = exp(-2|x|): ~1e-7 absolute error (MUFU ex2 + one IEEE division),
+// tanh(x) = sign(x) * (1 - t) / (1 + t), t = exp(-2|x|): ~3e-7 absolute error (MUFU ex2 + MUFU rcp),
 // an order of magnitude fewer instructions than libdevice tanhf in the 32k-element-per-tile epilogue.
 __device__ __forceinline__ float tanh_fast(float x) {
   const float t = __expf(-2.0f * fabsf(x));
-  return copysignf(__fdiv_rn(1.0f - t, 1.0f + t), x);
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -92,7 +93,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & kTf32Mask);  // round-to-nearest TF32 (no bias)
 }
 
-struct __align__(8) Barriers {
+struct __align__(16) Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t tmem_full[2];
@@ -100,14 +101,17 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
   uint32_t pad_[3];
   float bias[BN];  // epilogue reads the bias through shared memory (broadcast LDS) instead of 64 dependent LDGs / tile
+  // per-epilogue-warp transpose staging [warp][hi|lo][32 rows][8 float4], 16-byte chunks XOR-swizzled by row & 7
+  float4 stage[4][2][32][8];
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B tiles need 1024-byte alignment; pointer arithmetic (no integer round trip) keeps the shared
+  // address space visible to the compiler (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,59 +203,71 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t bph = (tcount >> 1) & 1u;
       tma::mbar_wait(&bars->tmem_full[buf], bph);
       fence_after_sync();
-      const int64_t row = tile * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      float4 (*sh)[8] = bars->stage[warp - 2][0];
+      float4 (*sl)[8] = bars->stage[warp - 2][1];
+      const int64_t row0 = tile * BM + q * 32;   // first row of this warp's 32-row slab
+      const int rs = lane >> 3, c4 = lane & 7;     // transposed phase: 4 rows x 8 float4 per instruction
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);  // asynchronous until tmem_ld_wait
-        // dgrad: fetch this row's 32 previous-activation values (hi + lo) while the TMEM load is in flight
-        float4 hv[8];
-        if (p.epi == EPI_TANHGRAD_SPLIT && row_ok) {
-          const float4* hh = reinterpret_cast<const float4*>(p.h_hi + row * BN + c0);
-          const float4* hl = reinterpret_cast<const float4*>(p.h_lo + row * BN + c0);
-          float4 a[8], b[8];
+        if (p.epi == EPI_TANHGRAD_SPLIT) {
+          // previous activation h = hi + lo of this warp's [32 x 32] block: coalesced 128-byte row segments
+          // (4 rows per instruction), transposed through shared memory to one row per thread
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = __ldg(hh + j);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) b[j] = __ldg(hl + j);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hv[j] = make_float4(a[j].x + b[j].x, a[j].y + b[j].y, a[j].z + b[j].z, a[j].w + b[j].w);
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rs;
+            const int64_t gr = row0 + rr;
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < p.M) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.h_hi + gr * BN + c0) + c4);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.h_lo + gr * BN + c0) + c4);
+              h = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            }
+            sh[rr][c4 ^ (rr & 7)] = h;
+          }
+          __syncwarp();
         }
         tmem_ld_wait();
-        if (row_ok) {
-          float* out_hi = p.c_hi + row * BN + c0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float v[4], hi[4], lo[4];
           if (p.epi == EPI_STORE) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(out_hi + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            for (int e = 0; e < 4; ++e) hi[e] = __uint_as_float(r[j4 * 4 + e]);
           } else {
-            float* out_lo = p.c_lo + row * BN + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float v[4], hi[4], lo[4];
-              if (p.epi == EPI_BIAS_TANH_SPLIT) {
-                const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j]);
-                v[0] = tanh_fast(__uint_as_float(r[j]) + b.x);
-                v[1] = tanh_fast(__uint_as_float(r[j + 1]) + b.y);
-                v[2] = tanh_fast(__uint_as_float(r[j + 2]) + b.z);
-                v[3] = tanh_fast(__uint_as_float(r[j + 3]) + b.w);
-              } else {
-                const float4 h = hv[j >> 2];
-                v[0] = __uint_as_float(r[j]) * (1.0f - h.x * h.x);
-                v[1] = __uint_as_float(r[j + 1]) * (1.0f - h.y * h.y);
-                v[2] = __uint_as_float(r[j + 2]) * (1.0f - h.z * h.z);
-                v[3] = __uint_as_float(r[j + 3]) * (1.0f - h.w * h.w);
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
-              *reinterpret_cast<float4*>(out_hi + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(out_lo + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            if (p.epi == EPI_BIAS_TANH_SPLIT) {
+              const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j4 * 4]);
+              v[0] = tanh_fast(__uint_as_float(r[j4 * 4 + 0]) + b.x);
+              v[1] = tanh_fast(__uint_as_float(r[j4 * 4 + 1]) + b.y);
+              v[2] = tanh_fast(__uint_as_float(r[j4 * 4 + 2]) + b.z);
+              v[3] = tanh_fast(__uint_as_float(r[j4 * 4 + 3]) + b.w);
+            } else {
+              const float4 h = sh[lane][j4 ^ (lane & 7)];  // row `lane` is private to thread `lane` in this phase
+              v[0] = __uint_as_float(r[j4 * 4 + 0]) * (1.0f - h.x * h.x);
+              v[1] = __uint_as_float(r[j4 * 4 + 1]) * (1.0f - h.y * h.y);
+              v[2] = __uint_as_float(r[j4 * 4 + 2]) * (1.0f - h.z * h.z);
+              v[3] = __uint_as_float(r[j4 * 4 + 3]) * (1.0f - h.w * h.w);
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+            sl[lane][j4 ^ (lane & 7)] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          sh[lane][j4 ^ (lane & 7)] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        }
+        __syncwarp();
+        // transposed stores: every instruction writes 4 complete 128-byte row segments (no partial sectors)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rs;
+          const int64_t gr = row0 + rr;
+          if (gr < p.M) {
+            reinterpret_cast<float4*>(p.c_hi + gr * BN + c0)[c4] = sh[rr][c4 ^ (rr & 7)];
+            if (p.epi != EPI_STORE) reinterpret_cast<float4*>(p.c_lo + gr * BN + c0)[c4] = sl[rr][c4 ^ (rr & 7)];
           }
         }
+        __syncwarp();
       }
       fence_before_sync();
       __syncwarp();
@@ -284,12 +300,13 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
          (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kWgradThreads = 192;
+__global__ void __launch_bounds__(kWgradThreads, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_z_hi, const __grid_constant__ CUtensorMap tm_z_lo,
                     const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
                     float* __restrict__ dW, int64_t n, int IN, int kb_per_chunk) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int out_tile = blockIdx.x & 1, chunk = blockIdx.x >> 1;
@@ -446,7 +463,7 @@ int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float*
   if (!e) e = encode_sw128(&tb_lo, b_lo, BN, (uint64_t)p.K, BN);
   if (e) return RB200_E_UNSUPPORTED;
   static bool attr_done = false;
-  constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + BN * 4;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + (int)sizeof(Barriers);
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
@@ -477,7 +494,7 @@ int wgrad(const float* z_hi, const float* z_lo, const float* h_hi, const float* 
   if (!e) e = encode_sw128_box32(&th_lo, h_lo, (uint64_t)n, (uint64_t)IN);
   if (e) return RB200_E_UNSUPPORTED;
   static bool attr_done = false;
-  constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + BN * 4;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + (int)sizeof(Barriers);
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
@@ -488,7 +505,7 @@ int wgrad(const float* z_hi, const float* z_lo, const float* h_hi, const float* 
   if (chunks < 1) chunks = 1;
   if (chunks > n_kb) chunks = n_kb;
   const int kb_per_chunk = (n_kb + chunks - 1) / chunks;
-  tc_wgrad_kernel<<<2 * chunks, kThreads, kSmem, st>>>(tz_hi, tz_lo, th_hi, th_lo, dW, n, IN, kb_per_chunk);
+  tc_wgrad_kernel<<<2 * chunks, kWgradThreads, kSmem, st>>>(tz_hi, tz_lo, th_hi, th_lo, dW, n, IN, kb_per_chunk);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
