@@ -233,16 +233,19 @@ int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float* params, fl
 /* Forward for training: states [n,obs] (row i at idx?idx[i]:i), action [n,act] (same gather).
  * Writes logprobs [n,act], entropy [n,act] (NULL ok), values [n,value_dim] (NULL ok) and keeps
  * the activations needed by backward in `acts`. Hidden layers run on tcgen05 (3xTF32) when wsplit is given
- * and the layer's K is a multiple of 32 (layer 1 additionally needs idx == NULL). */
+ * and the layer's K is a multiple of 32 (layer 1 additionally needs idx == NULL). states_hi/states_lo (NULL ok):
+ * a cached rb200_split_tf32() copy of `states` (same rows), saves one split pass per call. */
 int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                      const float* states, const float* action, const int64_t* idx, int64_t n,
+                      const float* states, const float* states_hi, const float* states_lo,
+                      const float* action, const int64_t* idx, int64_t n,
                       float* logprobs, float* entropy, float* values, float* acts, float* work,
                       rb200_stream_t stream);
 
 /* Backward: given d_logprobs [n,act], d_entropy [n,act] or NULL, d_values [n,value_dim] or NULL,
  * ACCUMULATES (+=) parameter gradients into grads (flat, same layout). `acts` from forward. */
 int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                       const float* states, const float* action, const int64_t* idx, int64_t n,
+                       const float* states, const float* states_hi, const float* states_lo,
+                       const float* action, const int64_t* idx, int64_t n,
                        const float* d_logprobs, const float* d_entropy, const float* d_values,
                        const float* acts, float* work, float* grads, rb200_stream_t stream);
 
@@ -253,6 +256,9 @@ int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float
                      const float* states, const float* noise, uint64_t seed, uint64_t offset,
                      const uint64_t* counter_dev, int64_t n, float* action, float* logprobs, float* values,
                      float* work, rb200_stream_t stream);
+
+/* x[n] -> exact-TF32 pair hi[n], lo[n] with hi + lo ~= x (2^-22 relative); operands of the 3xTF32 GEMMs. */
+int rb200_split_tf32(const float* x, float* hi, float* lo, int64_t n, rb200_stream_t stream);
 
 /* 3xTF32 tensor-core GEMM building block of the MLP towers (unit-test entry):
  * C[M,256] = A[M,K] . B[256,K]^T, fp32 in/out, K % 32 == 0; `work` = 2*M*K + 512*K floats. */

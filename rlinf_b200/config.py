@@ -54,7 +54,7 @@ def synthetic_ppo_config(B=4096, T=512, obs_dim=128, action_dim=8, update_epoch=
                           "seed": 1234}},
         "rollout": {"pipeline_stage_num": 1, "enable_cuda_graph": True},
         "actor": {
-            "micro_batch_size": micro_batch_size or gbs, "global_batch_size": gbs, "seed": seed,
+            "micro_batch_size": micro_batch_size or gbs // world_size, "global_batch_size": gbs, "seed": seed,
             "model": {"model_type": "mlp_policy", "obs_dim": obs_dim, "action_dim": action_dim,
                       "num_action_chunks": 1, "hidden_dim": 256, "precision": "32", "add_value_head": True},
             "optim": {"lr": 3.0e-4, "value_lr": 3.0e-4, "adam_beta1": 0.9, "adam_beta2": 0.999, "adam_eps": 1.0e-8,

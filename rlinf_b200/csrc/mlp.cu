@@ -174,6 +174,8 @@ struct HeadBwdArgs {
   float* g_mb;              // [act] +=
   float* g_logstd;          // [act] +=
   float* g_vw3;             // [vdim,256] +=
+  float* g_b2;              // [256] += column sums of dz3 (bias gradient of backbone layer 3)
+  float* g_vb2;             // [256] += column sums of dy3 (value layer 3)
   int64_t n;
   int act, vdim;
 };
@@ -183,13 +185,16 @@ struct HeadBwdArgs {
 template <bool REG>
 __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
   extern __shared__ float sm[];
-  // layout: mw [act][256] | vw [vdim][256] | acc_mw [act][256] | acc_vw [vdim][256] | acc_mb[32] | acc_ls[32]
+  // layout: mw [act][256] | vw [vdim][256] | acc_mw [act][256] | acc_vw [vdim][256] | acc_mb[32] | acc_ls[32] |
+  //         acc_b2[256] | acc_vb2[256]
   float* s_mw = sm;
   float* s_vw = s_mw + p.act * kH;
   float* a_mw = s_vw + p.vdim * kH;
   float* a_vw = a_mw + p.act * kH;
   float* a_mb = a_vw + p.vdim * kH;
   float* a_ls = a_mb + 32;
+  float* a_b2 = a_ls + 32;
+  float* a_vb2 = a_b2 + kH;
   const bool has_v = p.d_values != nullptr;
   for (int i = threadIdx.x; i < p.act * kH; i += blockDim.x) {
     s_mw[i] = p.mw[i];
@@ -200,8 +205,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
     a_vw[i] = 0.f;
   }
   if (threadIdx.x < 64) a_mb[threadIdx.x] = 0.f;  // a_mb and a_ls are contiguous
+  for (int i = threadIdx.x; i < 2 * kH; i += blockDim.x) a_b2[i] = 0.f;  // a_b2 and a_vb2 are contiguous
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float cb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float rm[REG ? 8 : 1][8], rv[REG ? 2 : 1][8];
 #pragma unroll
   for (int a = 0; a < (REG ? 8 : 1); ++a)
@@ -259,6 +266,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
     o1.z = dh1.z * (1.f - h1.z * h1.z); o1.w = dh1.w * (1.f - h1.w * h1.w);
     store_split(p.dz3, p.dz3l, row * kH + lane * 4, o0);
     store_split(p.dz3, p.dz3l, row * kH + 128 + lane * 4, o1);
+    cb[0] += o0.x; cb[1] += o0.y; cb[2] += o0.z; cb[3] += o0.w;
+    cb[4] += o1.x; cb[5] += o1.y; cb[6] += o1.z; cb[7] += o1.w;
 
     if (has_v) {
       const float4 g0 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4),
@@ -293,6 +302,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
       q1.z = dg1.z * (1.f - g1.z * g1.z); q1.w = dg1.w * (1.f - g1.w * g1.w);
       store_split(p.dy3, p.dy3l, row * kH + lane * 4, q0);
       store_split(p.dy3, p.dy3l, row * kH + 128 + lane * 4, q1);
+      cv[0] += q0.x; cv[1] += q0.y; cv[2] += q0.z; cv[3] += q0.w;
+      cv[4] += q1.x; cv[5] += q1.y; cv[6] += q1.z; cv[7] += q1.w;
+    }
+  }
+  // bias gradients of the two layer-3 pre-activations (lane owns columns lane*4..+3 and 128+lane*4..+3)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&a_b2[lane * 4 + j], cb[j]);
+    atomicAdd(&a_b2[128 + lane * 4 + j], cb[4 + j]);
+    if (has_v) {
+      atomicAdd(&a_vb2[lane * 4 + j], cv[j]);
+      atomicAdd(&a_vb2[128 + lane * 4 + j], cv[4 + j]);
     }
   }
   if (REG) {
@@ -328,6 +349,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
   if (threadIdx.x < p.act) {
     atomicAdd(&p.g_mb[threadIdx.x], a_mb[threadIdx.x]);
     atomicAdd(&p.g_logstd[threadIdx.x], a_ls[threadIdx.x]);
+  }
+  for (int i = threadIdx.x; i < kH; i += blockDim.x) {
+    atomicAdd(&p.g_b2[i], a_b2[i]);
+    if (has_v) atomicAdd(&p.g_vb2[i], a_vb2[i]);
   }
 }
 
@@ -375,10 +400,14 @@ int layer_forward(const float* in_hi, const float* in_lo, const int64_t* idx, in
 }
 
 // X -> H1 -> H2 -> H3 (each [2][n,256])
-int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
-                  float* H1, float* H2, float* H3, float* xsplit, cudaStream_t st) {
-  int e = layer_forward(X, nullptr, idx, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr, ws ? ws->w0l : nullptr, H1,
-                        xsplit, st);
+int tower_forward(const float* X, const float* Xh, const float* Xl, const int64_t* idx, int64_t n, int in_dim,
+                  const TowerW& w, const TowerWS* ws, float* H1, float* H2, float* H3, float* xsplit, cudaStream_t st) {
+  // Xh/Xl: caller-provided exact-TF32 split of X (cached across epochs), else X is split on the fly into xsplit
+  int e = (Xh && Xl && !idx)
+              ? layer_forward(Xh, Xl, nullptr, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr, ws ? ws->w0l : nullptr,
+                              H1, xsplit, st)
+              : layer_forward(X, nullptr, idx, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr,
+                              ws ? ws->w0l : nullptr, H1, xsplit, st);
   if (e) return e;
   e = layer_forward(H1, H1 + n * kH, nullptr, n, kH, w.w1, w.b1, ws ? ws->w1h : nullptr, ws ? ws->w1l : nullptr, H2,
                     xsplit, st);
@@ -388,7 +417,8 @@ int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, con
 }
 
 // backward through the three hidden layers of one tower, given dZ3 (hi,lo). tmpA/tmpB: [2][n,256] scratch.
-int tower_backward(const float* X, const float* xsplit, const int64_t* idx, int64_t n, int in_dim, const TowerW& w,
+int tower_backward(const float* X, const float* xs_hi, const float* xs_lo, const int64_t* idx, int64_t n, int in_dim,
+                   const TowerW& w,
                    const TowerWS* ws, const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB,
                    float* g_w0,
                    float* g_b0, float* g_w1, float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
@@ -399,12 +429,12 @@ int tower_backward(const float* X, const float* xsplit, const int64_t* idx, int6
   const int64_t L = n * kH;  // offset of the lo part
   int e;
   auto wgrad = [&](const float* dZ, const float* Hin, const float* Hin_lo, const int64_t* in_rows, int in_ld,
-                   float* gw, float* gb) -> int {
+                   float* gw, float* gb, bool need_colsum) -> int {
     // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
     const int64_t cs_rows_ = cs_rows;
     if (ws && Hin_lo && !in_rows && (in_ld % rb::tc::BK == 0) && in_ld <= 256) {  // tensor cores (3xTF32)
       int ee = rb::tc::wgrad(dZ, dZ + L, Hin, Hin_lo, gw, n, in_ld, st);
-      if (ee) return ee;
+      if (ee || !need_colsum) return ee;
       colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows_);
       rb::count_launch();
       cudaError_t ce = cudaPeekAtLastError();
@@ -415,18 +445,18 @@ int tower_backward(const float* X, const float* xsplit, const int64_t* idx, int6
     g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = Hin; g.B2 = Hin_lo; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw;
     g.ldc = in_ld; g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
     int ee = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(g, splits, st);
-    if (ee) return ee;
+    if (ee || !need_colsum) return ee;
     colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows);
     rb::count_launch();
     cudaError_t ce = cudaPeekAtLastError();
     return ce == cudaSuccess ? 0 : (int)ce;
   };
   auto dgrad = [&](const float* dZ, const float* W, const float* Wth, const float* Wtl, const float* Hprev,
-                   float* out) -> int {
-    // out(hi,lo) = split( (dZ . W) * (1 - Hprev^2) )
+                   float* out, float* gb_prev) -> int {
+    // out(hi,lo) = split( (dZ . W) * (1 - Hprev^2) ); the tensor-core epilogue also adds out's column sums to gb_prev
     if (Wth) {
       rb::tc::Params p{};
-      p.M = n; p.K = kH; p.h_hi = Hprev; p.h_lo = Hprev + L; p.c_hi = out; p.c_lo = out + L;
+      p.M = n; p.K = kH; p.h_hi = Hprev; p.h_lo = Hprev + L; p.c_hi = out; p.c_lo = out + L; p.colsum = gb_prev;
       p.epi = rb::tc::EPI_TANHGRAD_SPLIT;
       return rb::tc::launch(dZ, dZ + L, Wth, Wtl, p, st);
     }
@@ -437,13 +467,14 @@ int tower_backward(const float* X, const float* xsplit, const int64_t* idx, int6
     if (ee) return ee;
     return rb::tc::split(out, out, out + L, L, st);
   };
-  if ((e = wgrad(dZ3, H2, H2 + L, nullptr, kH, g_w2, g_b2))) return e;
-  if ((e = dgrad(dZ3, w.w2, ws ? ws->w2th : nullptr, ws ? ws->w2tl : nullptr, H2, tmpA))) return e;  // dZ2
-  if ((e = wgrad(tmpA, H1, H1 + L, nullptr, kH, g_w1, g_b1))) return e;
-  if ((e = dgrad(tmpA, w.w1, ws ? ws->w1th : nullptr, ws ? ws->w1tl : nullptr, H1, tmpB))) return e;  // dZ1
-  if (ws && xsplit && !idx && in_dim % rb::tc::BK == 0)  // forward left the exact-TF32 split of X in `work`
-    return wgrad(tmpB, xsplit, xsplit + n * in_dim, nullptr, in_dim, g_w0, g_b0);
-  return wgrad(tmpB, X, nullptr, idx, in_dim, g_w0, g_b0);
+  const bool tc = ws != nullptr;  // tensor-core dgrad adds the bias gradients of layers 2 and 1 in its epilogue
+  if ((e = wgrad(dZ3, H2, H2 + L, nullptr, kH, g_w2, g_b2, false))) return e;  // g_b2: head_bwd_kernel
+  if ((e = dgrad(dZ3, w.w2, ws ? ws->w2th : nullptr, ws ? ws->w2tl : nullptr, H2, tmpA, g_b1))) return e;  // dZ2
+  if ((e = wgrad(tmpA, H1, H1 + L, nullptr, kH, g_w1, g_b1, !tc))) return e;
+  if ((e = dgrad(tmpA, w.w1, ws ? ws->w1th : nullptr, ws ? ws->w1tl : nullptr, H1, tmpB, g_b0))) return e;  // dZ1
+  if (ws && xs_hi && xs_lo && !idx && in_dim % rb::tc::BK == 0)  // exact-TF32 split of X (from forward / the caller)
+    return wgrad(tmpB, xs_hi, xs_lo, nullptr, in_dim, g_w0, g_b0, !tc);
+  return wgrad(tmpB, X, nullptr, idx, in_dim, g_w0, g_b0, !tc);
 }
 
 }  // namespace
@@ -542,7 +573,8 @@ extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float*
 }
 
 extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                                 const float* states, const float* action, const int64_t* idx, int64_t n,
+                                 const float* states, const float* states_hi, const float* states_lo,
+                                 const float* action, const int64_t* idx, int64_t n,
                                  float* logprobs, float* entropy, float* values, float* acts, float* work,
                                  rb200_stream_t stream) {
   int e = check_layout(L);
@@ -558,11 +590,11 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params,
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3, xsplit,
-                         st)))
+  if ((e = tower_forward(states, states_hi, states_lo, idx, n, L->obs_dim, tower_w(L, P, false),
+                         wsplit ? &bws : nullptr, H1, H2, H3, xsplit, st)))
     return e;
-  if (values &&
-      (e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
+  if (values && (e = tower_forward(states, states_hi, states_lo, idx, n, L->obs_dim, tower_w(L, P, true),
+                                   wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
     return e;
   HeadFwdArgs h{};
   h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
@@ -575,7 +607,8 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params,
 }
 
 extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                                  const float* states, const float* action, const int64_t* idx, int64_t n,
+                                  const float* states, const float* states_hi, const float* states_lo,
+                                  const float* action, const int64_t* idx, int64_t n,
                                   const float* d_logprobs, const float* d_entropy, const float* d_values,
                                   const float* acts, float* work, float* grads, rb200_stream_t stream) {
   int e = check_layout(L);
@@ -594,8 +627,9 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.d_logprobs = d_logprobs;
   h.d_entropy = d_entropy; h.d_values = d_values; h.dz3 = dZ3; h.dz3l = dZ3 + n * kH; h.dy3 = dY3; h.dy3l = dY3 + n * kH;
   h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
+  h.g_b2 = G + L->bb2; h.g_vb2 = G + L->vb2;
   h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
-  const size_t smem = sizeof(float) * ((size_t)2 * (L->act_dim + L->value_dim) * kH + 64);
+  const size_t smem = sizeof(float) * ((size_t)2 * (L->act_dim + L->value_dim) * kH + 64 + 2 * kH);
   const bool reg = L->act_dim <= 8 && L->value_dim <= 2;
   if (smem > 48 * 1024) {
     cudaError_t ce = cudaFuncSetAttribute(head_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -613,13 +647,15 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   }
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  const float* xsplit = work + 6 * PF;  // written by rb200_mlp_forward (same `work` buffer), untouched since
-  if ((e = tower_backward(states, xsplit, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, dZ3,
-                          tA, tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
+  // exact-TF32 split of the input states: the caller's cached copy, else what rb200_mlp_forward left in `work`
+  const float* xs_hi = states_hi ? states_hi : work + 6 * PF;
+  const float* xs_lo = states_lo ? states_lo : work + 6 * PF + n * L->obs_dim;
+  if ((e = tower_backward(states, xs_hi, xs_lo, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2,
+                          dZ3, tA, tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
     return e;
   if (d_values &&
-      (e = tower_backward(states, xsplit, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, dY3, uA,
-                          uB,
+      (e = tower_backward(states, xs_hi, xs_lo, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2,
+                          dY3, uA, uB,
                           G + L->vw0, G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
     return e;
   return RB200_OK;
@@ -641,11 +677,11 @@ extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, 
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3,
-                         xsplit, st)))
+  if ((e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, P, false),
+                         wsplit ? &bws : nullptr, H1, H2, H3, xsplit, st)))
     return e;
-  if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2,
-                                   G3, xsplit, st)))
+  if (values && (e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, P, true),
+                                   wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
     return e;
   HeadFwdArgs h{};
   h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
@@ -693,10 +729,18 @@ extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, c
   float *G1 = work, *G2 = G1 + PF, *G3 = G2 + PF;
   float* xsplit = G3 + PF;
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, params, true), wsplit ? &vws : nullptr, G1, G2, G3,
-                         xsplit, st)))
+  if ((e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, params, true),
+                         wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
     return e;
   value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, G3 + n * kH, params + L->vw3, values, n, L->value_dim);
   rb::count_launch();
   RB_RETURN_LAUNCH();
+}
+
+// x -> exact-TF32 (hi, lo) pair (hi + lo ~= x to 2^-22). Lets the caller split the shuffled observations once per
+// iteration instead of once per forward call.
+extern "C" int rb200_split_tf32(const float* x, float* hi, float* lo, int64_t n, rb200_stream_t stream) {
+  if (!x || !hi || !lo) return RB200_E_NULL;
+  if (n <= 0) return RB200_E_SHAPE;
+  return rb::tc::split(x, hi, lo, n, rb::as_stream(stream));
 }

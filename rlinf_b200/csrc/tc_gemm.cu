@@ -100,7 +100,9 @@ struct __align__(16) Barriers {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  float bias[BN];  // epilogue reads the bias through shared memory (broadcast LDS) instead of 64 dependent LDGs / tile
+  // forward epilogue: the layer bias (broadcast LDS instead of 64 dependent LDGs / tile);
+  // dgrad epilogue: per-CTA column sums of the output tiles (bias gradient), flushed once at kernel end
+  float bias[BN];
   // per-epilogue-warp transpose staging [warp][hi|lo][32 rows][8 float4], 16-byte chunks XOR-swizzled by row & 7
   float4 stage[4][2][32][8];
 };
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (p.epi == EPI_BIAS_TANH_SPLIT)
     for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = p.bias[i];
+  else
+    for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -257,6 +261,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           sh[lane][j4 ^ (lane & 7)] = make_float4(hi[0], hi[1], hi[2], hi[3]);
         }
         __syncwarp();
+        if (p.colsum != nullptr && p.epi == EPI_TANHGRAD_SPLIT) {
+          // bias gradient of the layer that produced this tile: column sums over the warp's 32 rows (rows beyond M
+          // hold exact zeros), one vector-free atomic per column per chunk
+          const int ch = lane >> 2, el = lane & 3;
+          float cs = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const float* ph = reinterpret_cast<const float*>(&sh[rr][ch ^ (rr & 7)]);
+            const float* pl = reinterpret_cast<const float*>(&sl[rr][ch ^ (rr & 7)]);
+            cs += ph[el] + pl[el];
+          }
+          atomicAdd(&bars->bias[c0 + lane], cs);  // shared-memory atomic (4 warps per address)
+        }
         // transposed stores: every instruction writes 4 complete 128-byte row segments (no partial sectors)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -278,6 +295,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   // ---- teardown ----
   fence_before_sync();
   __syncthreads();
+  if (p.colsum != nullptr && p.epi == EPI_TANHGRAD_SPLIT)
+    for (int i = threadIdx.x; i < BN; i += kThreads)
+      if (bars->bias[i] != 0.f) atomicAdd(p.colsum + i, bars->bias[i]);
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);

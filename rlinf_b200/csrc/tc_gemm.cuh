@@ -18,6 +18,7 @@ struct Params {
   const float* h_lo;
   float* c_hi;        // [M,256] (EPI_STORE: plain fp32 result)
   float* c_lo;        // [M,256]
+  float* colsum;      // [256] += column sums of the output (bias gradient of the producing layer), or NULL
   int epi;
 };
 
