@@ -297,6 +297,26 @@ int rb200_bootstrap_rewards(float* rewards, const float* final_values, const uin
 /* counter_dev[0] += inc (device-side RNG step counter so captured CUDA graphs replay fresh noise). */
 int rb200_counter_add(uint64_t* counter_dev, uint64_t inc, rb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a10 reward filter: replaces the filter_rewards block of EmbodiedFSDPActor._process_received_rollout_batch,
+ *   workers/actor/embodied_fsdp_actor_worker.py:236-282 (= preprocess_embodied_batch, rlinf/utils/utils.py:803-830).
+ *   rewards f32 [nc,B,C]; loss_mask bool [nc,B,C] or NULL; keep_env bool [B] (scratch/out);
+ *   out_mask bool [nc,B,C] (= keep & loss_mask) or [nc,B,1] when loss_mask is NULL.
+ * ---------------------------------------------------------------------------------------- */
+int rb200_reward_filter(const float* rewards, const uint8_t* loss_mask, uint8_t* out_mask, uint8_t* keep_env,
+                        int nc, int B, int C, int group_size, float lower, float upper,
+                        rb200_stream_t stream);
+
+/* a18 kl_penalty (rlinf/algorithms/utils.py:26-64): mode 0 k1/kl, 1 abs, 2 k2/mse, 3 k3/low_var_kl.
+ * out[n] = penalty, d_logprob[n] (NULL ok) = d penalty / d logprob. */
+int rb200_kl_penalty(const float* logprob, const float* ref_logprob, float* out, float* d_logprob, int64_t n,
+                     int mode, rb200_stream_t stream);
+
+/* a24 masked statistics for compute_rollout_metrics (rlinf/utils/metric_utils.py:422-506):
+ * out4 = {count, sum, min, max} of x[i] over entries with mask[i / mask_div] != 0 (mask NULL = all). */
+int rb200_masked_stats(const float* x, const uint8_t* mask, int64_t n, int64_t mask_div, double* out4,
+                       rb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,6 +234,32 @@ def reward_filter_mask(rewards, loss_mask, group_size, lower, upper):
     return (keep & loss_mask) if loss_mask is not None else keep
 
 
+def rollout_metrics(buf: dict) -> dict:
+    """rlinf/utils/metric_utils.py:422-506 (compute_rollout_metrics) for one rank."""
+    mask = buf.get("loss_mask")
+
+    def valid(x):
+        if mask is None:
+            return x.reshape(-1)
+        m = mask.bool()
+        if m.ndim == x.ndim - 1:
+            m = m.unsqueeze(-1)
+        return x[torch.broadcast_to(m, x.shape)]
+
+    out = {}
+    if "rewards" in buf:
+        v = valid(buf["rewards"])
+        out["rewards"] = float(v.float().sum() / v.numel()) if v.numel() else float("nan")
+    for k in ("advantages", "returns"):
+        if buf.get(k) is not None:
+            v = valid(buf[k])
+            if v.numel():
+                out[f"{k}_mean"], out[f"{k}_max"], out[f"{k}_min"] = float(v.float().sum() / v.numel()), float(v.max()), float(v.min())
+            else:
+                out[f"{k}_mean"] = out[f"{k}_max"] = out[f"{k}_min"] = float("nan")
+    return out
+
+
 # --------------------------------------------------------------------------
 # trajectory indexing
 # --------------------------------------------------------------------------

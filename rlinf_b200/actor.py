@@ -108,8 +108,9 @@ class EmbodiedActor:
             rollout_batch["loss_mask"] = loss_mask
             rollout_batch["loss_mask_sum"] = loss_mask_sum
         if cfg.algorithm.get("filter_rewards", False):
-            raise NotImplementedError("algorithm.filter_rewards (embodied_fsdp_actor_worker.py:236-282) is not "
-                                      "implemented in this round")
+            rollout_batch["loss_mask"] = ops.reward_filter(
+                rollout_batch["rewards"], rollout_batch.get("loss_mask", None), cfg.algorithm.group_size,
+                cfg.algorithm.rewards_lower_bound, cfg.algorithm.rewards_upper_bound)
         return rollout_batch
 
     # ---- advantages -------------------------------------------------------------------------------
@@ -125,7 +126,11 @@ class EmbodiedActor:
             "advantage_mode": cfg.algorithm.get("advantage_mode", None),
         }
         rb.update(calculate_adv_and_returns(**kwargs))
-        return {}
+        if not cfg.runner.get("rollout_metrics", True):
+            return {}
+        from .metric_utils import compute_rollout_metrics
+
+        return compute_rollout_metrics(rb, self._world_size, self.pg)
 
     # ---- training ---------------------------------------------------------------------------------
     def _shuffle_id(self, n: int) -> torch.Tensor:

@@ -112,3 +112,24 @@ def safe_normalize(array: torch.Tensor, loss_mask: Optional[torch.Tensor], stats
     if stats is None:
         raise ValueError("safe_normalize needs the {n,sum,sumsq} statistics produced by the scan kernel")
     return ops.normalize_(array, stats, 1e-5)
+
+
+class _KlPenalty(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logprob, ref_logprob, kind):
+        out, g = ops.kl_penalty_raw(logprob.detach(), ref_logprob.detach(), kind, want_grad=logprob.requires_grad)
+        ctx.save_for_backward(g)
+        return out.view(logprob.shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        return (grad_out * g.view(grad_out.shape)) if g is not None else None, None, None
+
+
+def kl_penalty(logprob: torch.Tensor, ref_logprob: torch.Tensor, kl_penalty: str) -> torch.Tensor:
+    """KL estimators k1/abs/k2/k3 (rlinf/algorithms/utils.py:26-64), one elementwise kernel (forward value and
+    d/dlogprob in the same pass); used as a loss term by the reasoning actor (fsdp_actor_worker.py:762-765)."""
+    if kl_penalty == "full":
+        raise NotImplementedError
+    return _KlPenalty.apply(logprob, ref_logprob, kl_penalty)

@@ -168,3 +168,46 @@ def scale_by_(x: torch.Tensor, s_dev: torch.Tensor) -> torch.Tensor:
     s = s_dev.reshape(1).to(torch.float32)
     L.check(lib.rb200_scale_by(L.ptr(x), x.numel(), L.ptr(s), L.stream_ptr()), "scale_by")
     return x
+
+
+def reward_filter(rewards, loss_mask, group_size, lower, upper):
+    """filter_rewards (embodied_fsdp_actor_worker.py:236-282): returns the new loss_mask (bool) -
+    [nc,B,C] = keep & loss_mask, or [nc,B,1] when there was no loss_mask."""
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32)
+    m = L.as_u8(L.to_device(loss_mask, r.device))
+    nc, B, Cc = r.shape
+    if B % group_size != 0:
+        raise AssertionError(f"batch {B} not divisible by group_size {group_size}")
+    out = torch.empty((nc, B, Cc if m is not None else 1), dtype=torch.uint8, device=r.device)
+    keep = torch.empty((B,), dtype=torch.uint8, device=r.device)
+    L.check(lib.rb200_reward_filter(L.ptr(r), L.ptr(m), L.ptr(out), L.ptr(keep), nc, B, Cc, int(group_size),
+                                    float(lower), float(upper), L.stream_ptr()), "reward_filter")
+    return out.view(torch.bool)
+
+
+_KL_MODES = {"kl": 0, "k1": 0, "abs": 1, "mse": 2, "k2": 2, "low_var_kl": 3, "k3": 3}
+
+
+def kl_penalty_raw(logprob, ref_logprob, kind, want_grad=False):
+    lib = L.load()
+    if kind not in _KL_MODES:
+        raise NotImplementedError(kind)
+    a = L.to_device(logprob, dtype=torch.float32)
+    b = L.to_device(ref_logprob, a.device, torch.float32)
+    out = torch.empty_like(a)
+    g = torch.empty_like(a) if want_grad else None
+    L.check(lib.rb200_kl_penalty(L.ptr(a), L.ptr(b), L.ptr(out), L.ptr(g), a.numel(), _KL_MODES[kind],
+                                 L.stream_ptr()), "kl_penalty")
+    return out, g
+
+
+def masked_stats(x, mask=None, mask_div=1):
+    """{count, sum, min, max} (float64[4], device) of x over mask (mask index = flat index // mask_div)."""
+    lib = L.load()
+    xs = L.to_device(x, dtype=torch.float32).contiguous()
+    m = L.as_u8(L.to_device(mask, xs.device))
+    out = torch.empty(4, dtype=torch.float64, device=xs.device)
+    L.check(lib.rb200_masked_stats(L.ptr(xs), L.ptr(m.contiguous() if m is not None else None), xs.numel(),
+                                   int(mask_div), L.ptr(out), L.stream_ptr()), "masked_stats")
+    return out

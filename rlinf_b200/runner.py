@@ -56,8 +56,10 @@ class EmbodiedRunner:
 
     def update_phase(self, batch=None):
         self.actor.recv_rollout_trajectories(batch if batch is not None else self.buffer.as_batch())
-        self.actor.compute_advantages_and_returns()
-        return self.actor.run_training()
+        rollout_metrics = self.actor.compute_advantages_and_returns()
+        metrics = self.actor.run_training()
+        metrics.update({f"rollout/{k}": v for k, v in rollout_metrics.items()})
+        return metrics
 
     def run_iteration(self):
         self.actor.version = self.global_step

@@ -153,6 +153,40 @@ def gen_loss(ref, out):
         out[f"kl_{kind}"] = _np(ref.alg_utils.kl_penalty(a, b, kind))
 
 
+def gen_filter_and_metrics(ref, out):
+    import torch.distributed as dist
+    cases = []
+    for name, seed, nc, B, C, G, lo, hi, with_mask in [("f1", 0, 12, 32, 1, 8, -1.0, 1.0, True),
+                                                         ("f2", 1, 9, 24, 2, 4, -0.5, 2.0, False),
+                                                         ("f3", 2, 20, 64, 1, 8, 0.0, 100.0, True)]:
+        r, v, d = synth_rollout(seed, nc, B, C, 0.1)
+        batch = {"rewards": r, "dones": d}
+        res = ref.utils.preprocess_embodied_batch(batch, rollout_epoch=1, auto_reset=not with_mask,
+                                                  ignore_terminations=False, reward_type="action_level",
+                                                  filter_rewards=True, group_size=G, rewards_lower_bound=lo,
+                                                  rewards_upper_bound=hi)
+        out[f"filt_{name}_rewards"], out[f"filt_{name}_dones"] = _np(r), _np(d)
+        out[f"filt_{name}_cfg"] = np.array([G, lo, hi, int(with_mask)], dtype=np.float64)
+        out[f"filt_{name}_mask"] = _np(res["loss_mask"].contiguous())
+        cases.append(name)
+    out["filt_cases"] = np.array(cases)
+    # compute_rollout_metrics needs a process group: 1-rank gloo
+    if not dist.is_initialized():
+        import os
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    g = torch.Generator().manual_seed(21)
+    buf = {"rewards": torch.randn(16, 24, 1, generator=g), "advantages": torch.randn(16, 24, 1, generator=g),
+           "returns": torch.randn(16, 24, 1, generator=g), "loss_mask": torch.rand(16, 24, 1, generator=g) < 0.7}
+    m = ref.metric_utils.compute_rollout_metrics(buf)
+    for k, v in buf.items():
+        out["rm_" + k] = _np(v)
+    keys = sorted(m)
+    out["rm_keys"] = np.array(keys)
+    out["rm_vals"] = np.array([float(m[k]) for k in keys])
+
+
 def gen_indexing(ref, out):
     g = torch.Generator().manual_seed(9)
     T, B = 6, 10
@@ -228,7 +262,8 @@ def gen_policy(ref, out):
 def main():
     ref = load_reference()
     torch.set_num_threads(1)
-    for fn, name in ((gen_adv, "adv"), (gen_loss, "loss"), (gen_indexing, "indexing"), (gen_policy, "policy")):
+    for fn, name in ((gen_adv, "adv"), (gen_loss, "loss"), (gen_indexing, "indexing"), (gen_policy, "policy"),
+                     (gen_filter_and_metrics, "filter")):
         out = {}
         fn(ref, out)
         path = os.path.join(HERE, f"golden_{name}.npz")

@@ -92,7 +92,15 @@ def _stub_modules() -> None:
         sched.Worker = Worker
         sched.Channel = object
         sched.Cluster = object
+        sched.__path__ = []  # behave as a package so `rlinf.scheduler.worker.worker` can be stubbed too
         sys.modules["rlinf.scheduler"] = sched
+        wpkg = types.ModuleType("rlinf.scheduler.worker")
+        wpkg.__path__ = []
+        wmod = types.ModuleType("rlinf.scheduler.worker.worker")
+        wmod.Worker = Worker
+        wpkg.worker = wmod
+        sys.modules["rlinf.scheduler.worker"] = wpkg
+        sys.modules["rlinf.scheduler.worker.worker"] = wmod
 
 
 def _namespace(name: str, rel: str) -> None:

@@ -375,3 +375,45 @@ def test_mlp_sample_given_noise_vs_oracle():
     assert abs(z.mean().item()) < 0.05 and abs(z.std().item() - 1) < 0.05
     a3, _, _ = pol.sample(states.cuda().repeat(40, 1), seed=11, offset=0)
     assert torch.equal(a2, a3)
+
+
+def test_reward_filter_golden(golden):
+    from rlinf_b200 import ops
+
+    g = golden("filter")
+    for name in g["filt_cases"]:
+        G, lo, hi, with_mask = g[f"filt_{name}_cfg"]
+        r, d = _t(g[f"filt_{name}_rewards"]), _t(g[f"filt_{name}_dones"])
+        mask = ops.loss_mask(d)[0] if with_mask else None
+        out = ops.reward_filter(r, mask, int(G), float(lo), float(hi))
+        ref = _t(g[f"filt_{name}_mask"])
+        assert out.shape == ref.shape and torch.equal(out.cpu(), ref), name
+
+
+def test_rollout_metrics_golden(golden):
+    from rlinf_b200.metric_utils import compute_rollout_metrics
+
+    g = golden("filter")
+    buf = {k: _t(g["rm_" + k]).cuda() for k in ("rewards", "advantages", "returns", "loss_mask")}
+    m = compute_rollout_metrics(buf)
+    keys = [str(k) for k in g["rm_keys"]]
+    assert sorted(m) == keys
+    np.testing.assert_allclose([m[k] for k in keys], g["rm_vals"], rtol=1e-5, atol=1e-7)
+    m2 = compute_rollout_metrics({"rewards": buf["rewards"], "advantages": buf["advantages"]})
+    np.testing.assert_allclose(m2["advantages_max"], buf["advantages"].max().item())
+
+
+@pytest.mark.parametrize("kind", ["k1", "abs", "k2", "k3"])
+def test_kl_penalty_golden_and_grad(golden, kind):
+    import rlinf_b200.algorithms.utils as U
+
+    g = golden("loss")
+    a, b = _t(g["kl_a"]), _t(g["kl_b"])
+    ac = a.cuda().requires_grad_(True)
+    out = U.kl_penalty(ac, b.cuda(), kind)
+    torch.testing.assert_close(out.detach().cpu(), _t(g[f"kl_{kind}"]), rtol=1e-5, atol=1e-6)
+    w = torch.linspace(-1, 1, a.numel())
+    (out * w.cuda()).sum().backward()
+    ar = a.clone().requires_grad_(True)
+    (O.kl_penalty(ar, b, kind) * w).sum().backward()
+    torch.testing.assert_close(ac.grad.cpu(), ar.grad, rtol=1e-5, atol=1e-6)
