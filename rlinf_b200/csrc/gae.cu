@@ -95,14 +95,18 @@ __device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* 
 // Stage hand-off: full (TMA) -> dready (delta warps) -> gready (chain) -> empty (epilogue), all mbarriers.
 // Requires B % 16 == 0 (16-byte global strides for the byte tensors) and 16-byte aligned bases.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStagesWS = 8;
+// ncu (round 1): with [16 x 32] boxes every role spent its time waiting for TMA although DRAM, L2 and the TMA pipe
+// were all < 10 % busy - the TMA unit retires roughly one box per 200-350 cycles per SM regardless of box size
+// (same rate seen with the 4 KB boxes of tc_wgrad_kernel), so bandwidth comes from BIG boxes: 64 steps per stage.
+constexpr int kRW = 64;       // timesteps per TMA stage
+constexpr int kStagesWS = 4;  // 4 x 44.4 KB
 struct __align__(128) StageWS {
-  float r[kR][kW];
-  float v[kR + 1][kW];     // rows t0 .. t0+16 (the extra row is V[t+1] of the tile's last step)
-  uint8_t d[kR][kW];       // done AFTER step t (rows t0+1 .. t0+16 of dones)
-  uint8_t m[kR][kW];
-  float2 dc[kR][kW];       // {delta_t, c_t}
-  float g[kR][kW];
+  float r[kRW][kW];
+  float v[kRW + 1][kW];    // rows t0 .. t0+64 (the extra row is V[t+1] of the tile's last step)
+  uint8_t d[kRW][kW];      // done AFTER step t (rows t0+1 .. t0+64 of dones)
+  uint8_t m[kRW][kW];
+  float2 dc[kRW][kW];      // {delta_t, c_t}
+  float g[kRW][kW];
 };
 constexpr uint32_t kWsThreads = 192;
 
@@ -115,13 +119,14 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
                                                              double* __restrict__ stats, int T, int B, float gamma,
                                                              float coef) {
   extern __shared__ uint8_t smem_raw[];
-  StageWS* stages = reinterpret_cast<StageWS*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // pointer arithmetic without an integer round trip keeps the shared address space (LDS/STS, not generic LD/ST)
+  StageWS* stages = reinterpret_cast<StageWS*>(smem_raw + ((128u - (rb::tma::smem_u32(smem_raw) & 127u)) & 127u));
   __shared__ __align__(8) uint64_t full_bar[kStagesWS], dready_bar[kStagesWS], gready_bar[kStagesWS],
       empty_bar[kStagesWS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * kW;
-  const int n_iter = (T + kR - 1) / kR;
+  const int n_iter = (T + kRW - 1) / kRW;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -141,13 +146,13 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       rb::tma::prefetch_desc(&tm_d);
       if (HAS_V) rb::tma::prefetch_desc(&tm_v);
       if (HAS_MASK) rb::tma::prefetch_desc(&tm_m);
-      constexpr uint32_t kBytes = sizeof(float) * kR * kW + (HAS_V ? sizeof(float) * (kR + 1) * kW : 0) + kR * kW +
-                                  (HAS_MASK ? kR * kW : 0);
+      constexpr uint32_t kBytes = sizeof(float) * kRW * kW + (HAS_V ? sizeof(float) * (kRW + 1) * kW : 0) + kRW * kW +
+                                  (HAS_MASK ? kRW * kW : 0);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStagesWS;
         const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
         rb::tma::mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int t0 = T - (it + 1) * kR;  // may be negative on the last tile: OOB rows are zero-filled
+        const int t0 = T - (it + 1) * kRW;  // may be negative on the last tile: OOB rows are zero-filled
         rb::tma::mbar_arrive_expect_tx(&full_bar[s], kBytes);
         rb::tma::load_2d(&stages[s].r[0][0], &tm_r, col0, t0, &full_bar[s]);
         if (HAS_V) rb::tma::load_2d(&stages[s].v[0][0], &tm_v, col0, t0, &full_bar[s]);
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
       rb::tma::mbar_wait(&full_bar[s], ph);
       StageWS& st = stages[s];
-#pragma unroll
-      for (int k = 0; k < kR / 2; ++k) {
+#pragma unroll 8
+      for (int k = 0; k < kRW / 2; ++k) {
         const int rr = 2 * k + w;
         const float nd = st.d[rr][lane] ? 0.0f : 1.0f;
         float delta;
@@ -187,13 +192,16 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
       rb::tma::mbar_wait(&dready_bar[s], ph);
       StageWS& st = stages[s];
-      float2 dc[kR];
+#pragma unroll 1
+      for (int base = kRW - 16; base >= 0; base -= 16) {  // 16 steps at a time: loads hoisted above the chain
+        float2 dc[16];
 #pragma unroll
-      for (int rr = 0; rr < kR; ++rr) dc[rr] = st.dc[rr][lane];
+        for (int k = 0; k < 16; ++k) dc[k] = st.dc[base + k][lane];
 #pragma unroll
-      for (int rr = kR - 1; rr >= 0; --rr) {
-        g = __fadd_rn(dc[rr].x, __fmul_rn(dc[rr].y, g));
-        st.g[rr][lane] = g;
+        for (int k = 15; k >= 0; --k) {
+          g = __fadd_rn(dc[k].x, __fmul_rn(dc[k].y, g));
+          st.g[base + k][lane] = g;
+        }
       }
       __syncwarp();
       if (lane == 0) rb::tma::mbar_arrive(&gready_bar[s]);
@@ -207,11 +215,11 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kStagesWS;
       const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
-      const int t0 = T - (it + 1) * kR;
+      const int t0 = T - (it + 1) * kRW;
       rb::tma::mbar_wait(&gready_bar[s], ph);
       const StageWS& st = stages[s];
-#pragma unroll
-      for (int k = 0; k < kR / 2; ++k) {
+#pragma unroll 8
+      for (int k = 0; k < kRW / 2; ++k) {
         const int rr = 2 * k + w;
         const int t = t0 + rr;
         const float g = st.g[rr][lane];
@@ -338,10 +346,10 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
   const int grid = (B + kW - 1) / kW;
   if (aligned) {
     CUtensorMap tm_r, tm_v, tm_d, tm_m;
-    int e = rb::encode_tmap_2d(&tm_r, rewards, 4, (uint64_t)T, (uint64_t)B, kR, kW);
-    if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kR + 1, kW);
-    if (!e) e = rb::encode_tmap_2d(&tm_d, dones, 1, (uint64_t)T + 1, (uint64_t)B, kR, kW);
-    if (!e && HAS_MASK) e = rb::encode_tmap_2d(&tm_m, mask, 1, (uint64_t)T, (uint64_t)B, kR, kW);
+    int e = rb::encode_tmap_2d(&tm_r, rewards, 4, (uint64_t)T, (uint64_t)B, kRW, kW);
+    if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kRW + 1, kW);
+    if (!e) e = rb::encode_tmap_2d(&tm_d, dones, 1, (uint64_t)T + 1, (uint64_t)B, kRW, kW);
+    if (!e && HAS_MASK) e = rb::encode_tmap_2d(&tm_m, mask, 1, (uint64_t)T, (uint64_t)B, kRW, kW);
     if (!HAS_V) tm_v = tm_r;
     if (!HAS_MASK) tm_m = tm_d;
     if (!e) {

@@ -124,12 +124,13 @@ __device__ __forceinline__ RatioOut ratio_terms(float lp, float old_lp, float ad
 }
 
 template <bool TOKEN>
-__global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h, int U, int g,
+__global__ void __launch_bounds__(256, 3) ppo_main_kernel(rb200_ppo_args a, Hyper h, int U, int g,
                                                        double* __restrict__ sums) {
   __shared__ double red[S_NUM * 32];
-  double acc[S_NUM];
+  // per-thread partial sums in fp32 (a thread sees only a handful of units), widened to fp64 for the block/grid sums
+  float acc[S_NUM];
 #pragma unroll
-  for (int k = 0; k < S_NUM; ++k) acc[k] = 0.0;
+  for (int k = 0; k < S_NUM; ++k) acc[k] = 0.0f;
 
   const int64_t n_units = a.bsz * U;
   const bool has_mask = a.loss_mask != nullptr;
@@ -161,6 +162,9 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
     norm_adv = true;
   }
   const float scale = h.loss_scale;
+  const bool vec4 = ((g & 3) == 0) &&
+                    (((reinterpret_cast<uintptr_t>(a.logprobs) | reinterpret_cast<uintptr_t>(a.old_logprobs) |
+                       reinterpret_cast<uintptr_t>(a.d_logprobs)) & 15) == 0);
 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {
@@ -186,14 +190,14 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
         const RatioOut o = ratio_terms(lp_cur[k], lp_old[k], adv, m, h);
         const float term = ratio_agg ? __fmul_rn(__fdiv_rn(o.loss_e, w), mf) : __fmul_rn(o.loss_e, mf);
         const float term_abs = ratio_agg ? __fmul_rn(__fdiv_rn(fabsf(o.loss_e), w), mf) : __fmul_rn(fabsf(o.loss_e), mf);
-        acc[S_L] += (double)term;
-        acc[S_LABS] += (double)term_abs;
-        acc[S_RATIO] += (double)(o.ratio * mf);
-        acc[S_RABS] += (double)(fabsf(__fsub_rn(o.ratio, 1.0f)) * mf);
-        acc[S_CLIPPED] += (double)(o.clipped * mf);
-        acc[S_DUAL] += (double)(o.dual_ratio * mf);
-        acc[S_KL] += (double)o.lr_kl;
-        acc[S_CLIPFRAC] += (double)(o.clip_hit * mf);
+        acc[S_L] += term;
+        acc[S_LABS] += term_abs;
+        acc[S_RATIO] += (o.ratio * mf);
+        acc[S_RABS] += (fabsf(__fsub_rn(o.ratio, 1.0f)) * mf);
+        acc[S_CLIPPED] += (o.clipped * mf);
+        acc[S_DUAL] += (o.dual_ratio * mf);
+        acc[S_KL] += o.lr_kl;
+        acc[S_CLIPFRAC] += (o.clip_hit * mf);
         if (dlp) {
           const float cw = ratio_agg ? coef_actor / w : coef_actor;
           dlp[k] = h.critic_warmup ? 0.0f : scale * cw * o.dL_dlp;
@@ -201,25 +205,39 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
       }
     } else {
       float lp = 0.0f, old = 0.0f;
-      for (int k = 0; k < g; ++k) {
-        lp = __fadd_rn(lp, lp_cur[k]);
-        old = __fadd_rn(old, lp_old[k]);
+      if (vec4) {  // 16-byte loads, same left-to-right summation order
+        for (int k = 0; k < g; k += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(lp_cur + k);
+          const float4 o4 = __ldg(reinterpret_cast<const float4*>(lp_old + k));
+          lp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(lp, c4.x), c4.y), c4.z), c4.w);
+          old = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(old, o4.x), o4.y), o4.z), o4.w);
+        }
+      } else {
+        for (int k = 0; k < g; ++k) {
+          lp = __fadd_rn(lp, lp_cur[k]);
+          old = __fadd_rn(old, lp_old[k]);
+        }
       }
       const RatioOut o = ratio_terms(lp, old, adv, m, h);
       const float term = ratio_agg ? __fmul_rn(__fdiv_rn(o.loss_e, w), mf) : __fmul_rn(o.loss_e, mf);
       const float term_abs = ratio_agg ? __fmul_rn(__fdiv_rn(fabsf(o.loss_e), w), mf) : __fmul_rn(fabsf(o.loss_e), mf);
-      acc[S_L] += (double)term;
-      acc[S_LABS] += (double)term_abs;
-      acc[S_RATIO] += (double)(o.ratio * mf);
-      acc[S_RABS] += (double)(fabsf(__fsub_rn(o.ratio, 1.0f)) * mf);
-      acc[S_CLIPPED] += (double)(o.clipped * mf);
-      acc[S_DUAL] += (double)(o.dual_ratio * mf);
-      acc[S_KL] += (double)o.lr_kl;
-      acc[S_CLIPFRAC] += (double)(o.clip_hit * mf);
+      acc[S_L] += term;
+      acc[S_LABS] += term_abs;
+      acc[S_RATIO] += (o.ratio * mf);
+      acc[S_RABS] += (fabsf(__fsub_rn(o.ratio, 1.0f)) * mf);
+      acc[S_CLIPPED] += (o.clipped * mf);
+      acc[S_DUAL] += (o.dual_ratio * mf);
+      acc[S_KL] += o.lr_kl;
+      acc[S_CLIPFRAC] += (o.clip_hit * mf);
       if (dlp) {
         const float cw = ratio_agg ? coef_actor / w : coef_actor;
         const float gval = h.critic_warmup ? 0.0f : scale * cw * o.dL_dlp;
-        for (int k = 0; k < g; ++k) dlp[k] = gval;
+        if (vec4) {
+          const float4 g4 = make_float4(gval, gval, gval, gval);
+          for (int k = 0; k < g; k += 4) *reinterpret_cast<float4*>(dlp + k) = g4;
+        } else {
+          for (int k = 0; k < g; ++k) dlp[k] = gval;
+        }
       }
     }
 
@@ -233,14 +251,14 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
       const float lc = huber(e2, h.huber_delta, h.half_huber_delta);
       const float vl = fmaxf(lo, lc);
       const float term = has_mask ? (ratio_agg ? __fmul_rn(__fdiv_rn(vl, w), mf) : __fmul_rn(vl, mf)) : vl;
-      acc[S_VL] += (double)term;
-      acc[S_VCLIP] += (fabsf(__fsub_rn(vpc, pv)) > h.value_clip) ? 1.0 : 0.0;
+      acc[S_VL] += term;
+      acc[S_VCLIP] += (fabsf(__fsub_rn(vpc, pv)) > h.value_clip) ? 1.0f : 0.0f;
       if (m) {
-        acc[S_EV_N] += 1.0;
-        acc[S_EV_R] += (double)rt;
-        acc[S_EV_R2] += (double)__fmul_rn(rt, rt);
-        acc[S_EV_E] += (double)e1;
-        acc[S_EV_E2] += (double)__fmul_rn(e1, e1);
+        acc[S_EV_N] += 1.0f;
+        acc[S_EV_R] += rt;
+        acc[S_EV_R2] += __fmul_rn(rt, rt);
+        acc[S_EV_E] += e1;
+        acc[S_EV_E2] += __fmul_rn(e1, e1);
       }
       if (a.d_values) {
         const float g1 = lo > lc ? 1.0f : (lo == lc ? 0.5f : 0.0f);
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
       const float* en = a.entropy + u * g;
       float es = 0.0f;
       for (int k = 0; k < g; ++k) es = __fadd_rn(es, en[k]);
-      acc[S_ENT] += (double)(has_mask ? __fmul_rn(es, mf) : es);
+      acc[S_ENT] += (has_mask ? __fmul_rn(es, mf) : es);
       if (a.d_entropy) {
         const float cw = (has_mask ? coef_unit * mf : (float)(1.0 / (double)n_units));
         const float gval = (h.entropy_bonus > 0.0f && !h.critic_warmup) ? -scale * h.entropy_bonus * cw : 0.0f;
@@ -266,11 +284,14 @@ __global__ void __launch_bounds__(256) ppo_main_kernel(rb200_ppo_args a, Hyper h
     }
   }
 
-  rb::block_sum<S_NUM>(acc, red);
+  double accd[S_NUM];
+#pragma unroll
+  for (int k = 0; k < S_NUM; ++k) accd[k] = (double)acc[k];
+  rb::block_sum<S_NUM>(accd, red);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 1; k < S_NUM; ++k)  // slot 0 (mask count) belongs to the pre-pass
-      if (acc[k] != 0.0) atomicAdd(&sums[k], acc[k]);
+      if (accd[k] != 0.0) atomicAdd(&sums[k], accd[k]);
   }
 }
 
@@ -375,7 +396,7 @@ extern "C" int rb200_ppo_loss(const rb200_ppo_args* args, rb200_stream_t stream)
   RB_CHECK_CUDA(cudaMemsetAsync(a.workspace, 0, 32 * sizeof(double), st));
   const int64_t n_units = a.bsz * U;
   int64_t blocks = (n_units + 255) / 256;
-  const int64_t cap = (int64_t)rb::sm_count() * 4;
+  const int64_t cap = (int64_t)rb::sm_count() * 3;  // one resident wave at 3 blocks / SM (80 registers)
   if (blocks > cap) blocks = cap;
   if (a.loss_mask) {
     mask_count_kernel<<<(int)blocks, 256, 0, st>>>(a.loss_mask, a.idx, a.bsz, U, a.workspace);
