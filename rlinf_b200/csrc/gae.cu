@@ -85,11 +85,11 @@ __device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-pipelined, warp-specialised kernel. One CTA per 32 trajectories, 6 warps:
-//   warp 0      producer : one thread streams [16 steps x 32 traj] tiles (rewards, values(+1 row), dones, mask) with TMA
-//   warps 1,2   delta    : delta_t and the recurrence coefficient c_t = (gamma*lambda)*!done  (no dependence on g)
-//   warp 3      chain    : g_t = delta_t + c_t * g_{t+1}, strictly sequential, 2 dependent fp32 ops per step
-//   warps 4,5   epilogue : ret = g + V, adv = ret - V, coalesced 128-byte stores, statistics
+// TMA-pipelined, warp-specialised kernel. One CTA per 32 trajectories, 10 warps:
+//   warp 0      producer : one thread streams [64 steps x 32 traj] tiles (rewards, values(+1 row), dones, mask) with TMA
+//   warps 1-4   delta    : delta_t and the recurrence coefficient c_t = (gamma*lambda)*!done  (no dependence on g)
+//   warp 5      chain    : g_t = delta_t + c_t * g_{t+1}, strictly sequential, 2 dependent fp32 ops per step
+//   warps 6-9   epilogue : ret = g + V, adv = ret - V staged in smem, statistics, TMA tile stores
 // A single warp doing all of this is issue-bound (ncu round-1 v1: 46 us, ~107 cycles / step); splitting the work
 // that does not depend on the carry across warps leaves ~9 cycles / step on the sequential warp.
 // Stage hand-off: full (TMA) -> dready (delta warps) -> gready (chain) -> empty (epilogue), all mbarriers.
@@ -108,13 +108,17 @@ struct __align__(128) StageWS {
   float2 dc[kRW][kW];      // {delta_t, c_t}
   float g[kRW][kW];
 };
-constexpr uint32_t kWsThreads = 192;
+constexpr int kDW = 4;                  // delta warps
+constexpr int kEW = 4;                  // epilogue warps
+constexpr uint32_t kWsThreads = 32 * (1 + kDW + 1 + kEW);  // producer + delta + chain + epilogue = 320
 
 template <bool HAS_V, bool HAS_MASK, bool HAS_STATS>
 __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r,
                                                              const __grid_constant__ CUtensorMap tm_v,
                                                              const __grid_constant__ CUtensorMap tm_d,
                                                              const __grid_constant__ CUtensorMap tm_m,
+                                                             const __grid_constant__ CUtensorMap tm_adv,
+                                                             const __grid_constant__ CUtensorMap tm_ret,
                                                              float* __restrict__ adv, float* __restrict__ ret,
                                                              double* __restrict__ stats, int T, int B, float gamma,
                                                              float coef) {
@@ -132,9 +136,9 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
 #pragma unroll
     for (int s = 0; s < kStagesWS; ++s) {
       rb::tma::mbar_init(&full_bar[s], 1);
-      rb::tma::mbar_init(&dready_bar[s], 2);
+      rb::tma::mbar_init(&dready_bar[s], kDW);
       rb::tma::mbar_init(&gready_bar[s], 1);
-      rb::tma::mbar_init(&empty_bar[s], 2);
+      rb::tma::mbar_init(&empty_bar[s], 1);  // the epilogue warp that issued the tile's TMA stores
     }
     rb::tma::fence_barrier_init();
   }
@@ -160,8 +164,8 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
         if (HAS_MASK) rb::tma::load_2d(&stages[s].m[0][0], &tm_m, col0, t0, &full_bar[s]);
       }
     }
-  } else if (warp <= 2) {
-    // ---- delta warps: rows rr = w, w+2, ... of every tile ----
+  } else if (warp <= kDW) {
+    // ---- delta warps: rows rr = w, w+kDW, ... of every tile ----
     const int w = warp - 1;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kStagesWS;
@@ -169,8 +173,8 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       rb::tma::mbar_wait(&full_bar[s], ph);
       StageWS& st = stages[s];
 #pragma unroll 8
-      for (int k = 0; k < kRW / 2; ++k) {
-        const int rr = 2 * k + w;
+      for (int k = 0; k < kRW / kDW; ++k) {
+        const int rr = kDW * k + w;
         const float nd = st.d[rr][lane] ? 0.0f : 1.0f;
         float delta;
         if (HAS_V) {
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) rb::tma::mbar_arrive(&dready_bar[s]);
     }
-  } else if (warp == 3) {
+  } else if (warp == kDW + 1) {
     // ---- chain warp: the only sequential part ----
     float g = 0.0f;
     for (int it = 0; it < n_iter; ++it) {
@@ -207,41 +211,91 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
       if (lane == 0) rb::tma::mbar_arrive(&gready_bar[s]);
     }
   } else {
-    // ---- epilogue warps ----
-    const int w = warp - 4;
+    // ---- epilogue warps: warp e owns rows [16e, 16e+16) of every tile ----
+    // Round-1 measurements behind this shape: (1) per-row global stores cost ~45-90 issue cycles per warp
+    // instruction (time of v1-v3 == #STG per warp x ~60 cycles), so results are staged in shared memory (ret in
+    // place of g, adv in the dead delta/coef buffer) and leave as two TMA tile stores per 64-step tile; (2) with the
+    // stores gone the epilogue was issue-bound (~37 instructions per step on ONE warp per tile), hence 4 warps per
+    // tile and a branch-free statistics path.  A pure TMA pull of the same three inputs takes 8.3 us
+    // (tools/tma_probe.cu), so the loads are not what bounds this kernel.
+    const int e = warp - (kDW + 2);
     const int col = col0 + lane;
     const bool in_range = col < B;
     Acc acc_a, acc_r;
+    int rows_done = 0;
+    if (e == 0 && lane == 0) {
+      rb::tma::prefetch_desc(&tm_adv);
+      rb::tma::prefetch_desc(&tm_ret);
+    }
+    constexpr int kRE = kRW / kEW;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kStagesWS;
       const uint32_t ph = (uint32_t)(it / kStagesWS) & 1u;
       const int t0 = T - (it + 1) * kRW;
       rb::tma::mbar_wait(&gready_bar[s], ph);
-      const StageWS& st = stages[s];
-#pragma unroll 8
-      for (int k = 0; k < kRW / 2; ++k) {
-        const int rr = 2 * k + w;
-        const int t = t0 + rr;
-        const float g = st.g[rr][lane];
-        float rt, ad;
-        if (HAS_V) {
-          const float vt = st.v[rr][lane];
-          rt = __fadd_rn(g, vt);
-          ad = __fsub_rn(rt, vt);
-        } else {
-          rt = g;
-          ad = g;
+      StageWS& st = stages[s];
+      float (*adv_s)[kW] = reinterpret_cast<float (*)[kW]>(&st.dc[0][0]);  // [kRW][32] floats, 8 KB of the 16 KB
+      if (t0 >= 0) {
+#pragma unroll
+        for (int k = 0; k < kRE; ++k) {
+          const int rr = e * kRE + k;
+          const float g = st.g[rr][lane];
+          float rt, ad;
+          if (HAS_V) {
+            const float vt = st.v[rr][lane];
+            rt = __fadd_rn(g, vt);
+            ad = __fsub_rn(rt, vt);
+            st.g[rr][lane] = rt;
+          } else {
+            rt = g;
+            ad = g;
+          }
+          adv_s[rr][lane] = ad;
+          if (HAS_STATS) {
+            if (HAS_MASK) {
+              const bool valid = st.m[rr][lane] != 0;
+              acc_a.n += valid ? 1 : 0;
+              const float am = valid ? ad : 0.0f, rm = valid ? rt : 0.0f;
+              acc_a.ts += am;
+              acc_a.tss = fmaf(am, am, acc_a.tss);
+              acc_r.ts += rm;
+              acc_r.tss = fmaf(rm, rm, acc_r.tss);
+            } else {  // OOB columns were zero-filled by TMA: they add exact zeros, the count is fixed up below
+              acc_a.ts += ad;
+              acc_a.tss = fmaf(ad, ad, acc_a.tss);
+              acc_r.ts += rt;
+              acc_r.tss = fmaf(rt, rt, acc_r.tss);
+            }
+          }
         }
-        if (in_range && t >= 0) {
-          const size_t o = (size_t)t * B + col;
-          adv[o] = ad;
-          ret[o] = rt;
+        rows_done += kRE;
+      } else {
+        // ragged first tile (T % 64 != 0): plain stores for the rows that exist, no negative TMA store coordinates
+        for (int k = 0; k < kRE; ++k) {
+          const int rr = e * kRE + k;
+          const int t = t0 + rr;
+          if (t < 0) continue;
+          const float g = st.g[rr][lane];
+          float rt = g, ad = g;
+          if (HAS_V) {
+            const float vt = st.v[rr][lane];
+            rt = __fadd_rn(g, vt);
+            ad = __fsub_rn(rt, vt);
+          }
+          if (in_range) {
+            const size_t o = (size_t)t * B + col;
+            adv[o] = ad;
+            ret[o] = rt;
+          }
           if (HAS_STATS) {
             const bool valid = HAS_MASK ? (st.m[rr][lane] != 0) : true;
-            if (valid) {
-              acc_a.add(ad);
-              acc_r.add(rt);
-            }
+            if (HAS_MASK) acc_a.n += valid ? 1 : 0;
+            else rows_done += 1;
+            const float am = valid ? ad : 0.0f, rm = valid ? rt : 0.0f;
+            acc_a.ts += am;
+            acc_a.tss = fmaf(am, am, acc_a.tss);
+            acc_r.ts += rm;
+            acc_r.tss = fmaf(rm, rm, acc_r.tss);
           }
         }
       }
@@ -249,8 +303,23 @@ __global__ void __launch_bounds__(kWsThreads) gae_tma_kernel(const __grid_consta
         acc_a.fold();
         acc_r.fold();
       }
-      __syncwarp();
-      if (lane == 0) rb::tma::mbar_arrive(&empty_bar[s]);
+      rb::tma::fence_proxy_async();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");  // all four row groups of the tile are staged
+      if (e == (it % kEW) && lane == 0) {  // rotate the issuing warp so the smem-read wait is spread
+        if (t0 >= 0) {
+          rb::tma::store_2d(&tm_adv, &adv_s[0][0], col0, t0);  // cols >= B are clipped by TMA
+          rb::tma::store_2d(&tm_ret, &st.g[0][0], col0, t0);
+          rb::tma::store_commit();
+          rb::tma::store_wait_read();  // smem may be reused once the stores have read it
+        }
+        rb::tma::mbar_arrive(&empty_bar[s]);
+      }
+    }
+    if (lane == 0) rb::tma::store_wait_all();
+    if (HAS_STATS) {
+      if (!HAS_MASK) acc_a.n = in_range ? rows_done : 0;
+      else if (!in_range) acc_a.n = 0;  // mask bytes of OOB columns are zero-filled anyway
+      acc_r.n = acc_a.n;
     }
     if (HAS_STATS) flush_stats(acc_a, acc_r, stats);
   }
@@ -342,7 +411,8 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
   const bool aligned = (B % 16 == 0) && ((reinterpret_cast<uintptr_t>(rewards) & 15) == 0) &&
                        (!HAS_V || (reinterpret_cast<uintptr_t>(values) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(dones) & 15) == 0) &&
-                       (!HAS_MASK || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+                       (!HAS_MASK || (reinterpret_cast<uintptr_t>(mask) & 15) == 0) &&
+                       (((reinterpret_cast<uintptr_t>(adv) | reinterpret_cast<uintptr_t>(ret)) & 15) == 0);
   const int grid = (B + kW - 1) / kW;
   if (aligned) {
     CUtensorMap tm_r, tm_v, tm_d, tm_m;
@@ -350,6 +420,9 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
     if (!e && HAS_V) e = rb::encode_tmap_2d(&tm_v, values, 4, (uint64_t)T + 1, (uint64_t)B, kRW + 1, kW);
     if (!e) e = rb::encode_tmap_2d(&tm_d, dones, 1, (uint64_t)T + 1, (uint64_t)B, kRW, kW);
     if (!e && HAS_MASK) e = rb::encode_tmap_2d(&tm_m, mask, 1, (uint64_t)T, (uint64_t)B, kRW, kW);
+    CUtensorMap tm_adv, tm_ret;
+    if (!e) e = rb::encode_tmap_2d(&tm_adv, adv, 4, (uint64_t)T, (uint64_t)B, kRW, kW);
+    if (!e) e = rb::encode_tmap_2d(&tm_ret, ret, 4, (uint64_t)T, (uint64_t)B, kRW, kW);
     if (!HAS_V) tm_v = tm_r;
     if (!HAS_MASK) tm_m = tm_d;
     if (!e) {
@@ -362,7 +435,7 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
         attr_done = true;
       }
       gae_tma_kernel<HAS_V, HAS_MASK, HAS_STATS>
-          <<<grid, kWsThreads, kSmem, st>>>(tm_r, tm_v, tm_d, tm_m, adv, ret, stats, T, B, gamma, coef);
+          <<<grid, kWsThreads, kSmem, st>>>(tm_r, tm_v, tm_d, tm_m, tm_adv, tm_ret, adv, ret, stats, T, B, gamma, coef);
       rb::count_launch();
       RB_RETURN_LAUNCH();
     }
