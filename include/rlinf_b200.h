@@ -233,19 +233,17 @@ int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float* params, fl
 /* Forward for training: states [n,obs] (row i at idx?idx[i]:i), action [n,act] (same gather).
  * Writes logprobs [n,act], entropy [n,act] (NULL ok), values [n,value_dim] (NULL ok) and keeps
  * the activations needed by backward in `acts`. Hidden layers run on tcgen05 (3xTF32) when wsplit is given
- * and the layer's K is a multiple of 32 (layer 1 additionally needs idx == NULL). states_hi/states_lo (NULL ok):
- * a cached rb200_split_tf32() copy of `states` (same rows), saves one split pass per call. */
+ * and the layer's K is a multiple of 32 (layer 1 additionally needs idx == NULL). Activations are plain fp32; the
+ * tensor-core kernels split them into exact-TF32 (hi, lo) operands in shared memory. */
 int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                      const float* states, const float* states_hi, const float* states_lo,
-                      const float* action, const int64_t* idx, int64_t n,
+                      const float* states, const float* action, const int64_t* idx, int64_t n,
                       float* logprobs, float* entropy, float* values, float* acts, float* work,
                       rb200_stream_t stream);
 
 /* Backward: given d_logprobs [n,act], d_entropy [n,act] or NULL, d_values [n,value_dim] or NULL,
  * ACCUMULATES (+=) parameter gradients into grads (flat, same layout). `acts` from forward. */
 int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                       const float* states, const float* states_hi, const float* states_lo,
-                       const float* action, const int64_t* idx, int64_t n,
+                       const float* states, const float* action, const int64_t* idx, int64_t n,
                        const float* d_logprobs, const float* d_entropy, const float* d_values,
                        const float* acts, float* work, float* grads, rb200_stream_t stream);
 
@@ -257,18 +255,23 @@ int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float
                      const uint64_t* counter_dev, int64_t n, float* action, float* logprobs, float* values,
                      float* work, rb200_stream_t stream);
 
-/* x[n] -> exact-TF32 pair hi[n], lo[n] with hi + lo ~= x (2^-22 relative); operands of the 3xTF32 GEMMs. */
+/* x[n] -> exact-TF32 pair hi[n], lo[n] with hi + lo ~= x (2^-22 relative): the operand split of the 3xTF32 GEMMs
+ * (applied to the weights by rb200_mlp_prepare_weights and, on the fly, to activations inside the GEMM kernels). */
 int rb200_split_tf32(const float* x, float* hi, float* lo, int64_t n, rb200_stream_t stream);
 
 /* 3xTF32 tensor-core GEMM building block of the MLP towers (unit-test entry):
- * C[M,256] = A[M,K] . B[256,K]^T, fp32 in/out, K % 32 == 0; `work` = 2*M*K + 512*K floats. */
+ * C[M,256] = A[M,K] . B[256,K]^T, fp32 in/out, K % 32 == 0; `work` = 512*K floats (split copy of B). */
 int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M, int K, float* work,
                   rb200_stream_t stream);
 
 /* Weight-gradient counterpart (unit-test entry): dW[256,IN] += Z[n,256]^T . H[n,IN], IN % 32 == 0, IN <= 256;
- * `work` = 2*n*(256+IN) floats. */
+ * `work` is unused (may be NULL). */
 int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN, float* work,
                    rb200_stream_t stream);
+
+/* Experiment switches of the tensor-core kernels (tools/ only; default 0): bit 0 = additionally mask the streamed operand's
+ * hi part in shared memory (not needed: the tensor core truncates), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
+int rb200_debug_set_flags(int flags);
 
 /* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
  * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */

@@ -89,12 +89,13 @@ SIGNATURES = {
     "rb200_mlp_fwd_scratch_floats": (c_int64, [C.POINTER(MlpLayout), c_int64]),
     "rb200_mlp_wsplit_floats": (c_int64, [C.POINTER(MlpLayout)]),
     "rb200_mlp_prepare_weights": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p]),
-    "rb200_mlp_forward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 6),
-    "rb200_mlp_backward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 7),
+    "rb200_mlp_forward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 5 + [c_int64] + [c_void_p] * 6),
+    "rb200_mlp_backward": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 5 + [c_int64] + [c_void_p] * 7),
     "rb200_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "rb200_mlp_sample": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 4 + [c_uint64, c_uint64, c_void_p, c_int64] + [c_void_p] * 5),
     "rb200_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "rb200_tc_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "rb200_debug_set_flags": (c_int, [c_int]),
     "rb200_mlp_value": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rb200_synth_env_step": (c_int, [c_void_p] * 13 + [c_int] * 5 + [c_float] * 3 + [c_uint64, c_void_p, c_void_p]),
     "rb200_bootstrap_rewards": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),

@@ -151,8 +151,6 @@ class EmbodiedActor:
         shuffle_id = self._shuffle_id(rollout_size)
         batch = process_nested_dict_for_train(rb, shuffle_id)
         self.rollout_batch = batch
-        # observations are constant over the update epochs: split them once for the tensor-core GEMMs
-        self._states_split = self.model.split_states(batch["forward_inputs"]["states"])
         mbs = cfg.actor.micro_batch_size
         batch_size_per_rank, self.gradient_accumulation, n_global = D.per_rank_batch(
             cfg.actor.global_batch_size, self._world_size, mbs, rollout_size)
@@ -183,10 +181,8 @@ class EmbodiedActor:
         with_critic = cfg.algorithm.adv_type == "gae"
         ent_bonus = float(cfg.algorithm.get("entropy_bonus", 0) or 0)
         warm = self.optimizer_steps < self.critic_warmup_steps
-        ss = self._states_split
         out = self.model.forward_train(fi["states"][lo:hi], fi["action"][lo:hi], compute_entropy=ent_bonus > 0,
-                                       compute_values=with_critic,
-                                       states_split=None if ss is None else (ss[0][lo:hi], ss[1][lo:hi]))
+                                       compute_values=with_critic)
         A = cfg.actor.model.get("action_dim", 7)
         Cc = out["logprobs"].shape[1] // A
         U = 1 if cfg.algorithm.logprob_type == "chunk_level" else Cc

@@ -6,9 +6,9 @@
 //
 // Hidden-layer GEMMs run on the tensor cores (tc_gemm.cu: tcgen05 kind::tf32 with 3xTF32 compensation, fp32-level
 // accuracy) whenever the operand shapes allow TMA (K % 32 == 0, no row gather); the fp32 SIMT GEMM (sgemm.cuh)
-// covers the remaining shapes and the weight-gradient GEMMs (reduction over samples).  All activations and
-// activation-gradients are stored as exact-TF32 (hi, lo) pairs, x = hi + lo, so they can be fed to the tensor cores
-// without a conversion pass: 12 x [n,256] floats of tanh outputs (tanh' = 1 - h^2) per forward.
+// covers the remaining shapes.  Activations and activation-gradients are stored once, as plain fp32 [n,256]
+// (6 tanh outputs per forward, tanh' = 1 - h^2); the tensor-core kernels split them into exact-TF32 (hi, lo) pairs
+// on the fly in shared memory.
 // The heads (256 -> act mean, 256 -> value) are fused with the Normal log-prob / entropy epilogue and their backward.
 #include <curand_kernel.h>
 
@@ -21,8 +21,7 @@ namespace {
 using namespace rb::gemm;
 
 // out[n] += sum_m Z[m][n]   (bias gradients); Z is [M, N] with N <= 1024
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, const float* __restrict__ Z2,
-                                                     float* __restrict__ out, int64_t M, int N,
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, float* __restrict__ out, int64_t M, int N,
                                                      int64_t rows_per_block) {
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
@@ -30,12 +29,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int64_t r = r0;
     for (; r + 3 < r1; r += 4) {
-      s0 += Z[r * N + n] + Z2[r * N + n];
-      s1 += Z[(r + 1) * N + n] + Z2[(r + 1) * N + n];
-      s2 += Z[(r + 2) * N + n] + Z2[(r + 2) * N + n];
-      s3 += Z[(r + 3) * N + n] + Z2[(r + 3) * N + n];
+      s0 += Z[r * N + n];
+      s1 += Z[(r + 1) * N + n];
+      s2 += Z[(r + 2) * N + n];
+      s3 += Z[(r + 3) * N + n];
     }
-    for (; r < r1; ++r) s0 += Z[r * N + n] + Z2[r * N + n];
+    for (; r < r1; ++r) s0 += Z[r * N + n];
     atomicAdd(&out[n], (s0 + s1) + (s2 + s3));
   }
 }
@@ -48,25 +47,9 @@ constexpr int kMaxAct = 32;
 constexpr int kMaxVal = 8;
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
 
-__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & 0xffffe000u);  // round-to-nearest TF32
-}
-__device__ __forceinline__ void store_split(float* hi, float* lo, int64_t off, float4 v) {
-  float4 h, l;
-  split1(v.x, h.x, l.x);
-  split1(v.y, h.y, l.y);
-  split1(v.z, h.z, l.z);
-  split1(v.w, h.w, l.w);
-  *reinterpret_cast<float4*>(hi + off) = h;
-  *reinterpret_cast<float4*>(lo + off) = l;
-}
-
 struct HeadFwdArgs {
-  const float* h3;      // [n,256] backbone features, hi part
-  const float* h3l;     //         lo part
-  const float* g3;      // [n,256] value features hi (may be null -> no values)
-  const float* g3l;
+  const float* h3;      // [n,256] backbone features
+  const float* g3;      // [n,256] value features (may be null -> no values)
   const float* mw;      // [act,256]
   const float* mb;      // [act]
   const float* logstd;  // [act]
@@ -96,10 +79,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 h0 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4),
-                           *reinterpret_cast<const float4*>(p.h3l + row * kH + lane * 4));
-    const float4 h1 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4),
-                           *reinterpret_cast<const float4*>(p.h3l + row * kH + 128 + lane * 4));
+    const float4 h0 = *reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4);
+    const float4 h1 = *reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4);
     float my_mean = 0.f;
     for (int a = 0; a < p.act; ++a) {
       const float4 w0 = *reinterpret_cast<const float4*>(s_mw + a * kH + lane * 4);
@@ -136,10 +117,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
       if (p.mean_out) p.mean_out[row * p.act + lane] = my_mean;
     }
     if (p.g3 && p.values) {
-      const float4 g0 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4),
-                             *reinterpret_cast<const float4*>(p.g3l + row * kH + lane * 4));
-      const float4 g1 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4),
-                             *reinterpret_cast<const float4*>(p.g3l + row * kH + 128 + lane * 4));
+      const float4 g0 = *reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4);
+      const float4 g1 = *reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4);
       for (int c = 0; c < p.vdim; ++c) {
         const float4 w0 = *reinterpret_cast<const float4*>(s_vw + c * kH + lane * 4);
         const float4 w1 = *reinterpret_cast<const float4*>(s_vw + c * kH + 128 + lane * 4);
@@ -153,10 +132,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
 }
 
 struct HeadBwdArgs {
-  const float* h3;   // hi / lo parts of the layer-3 activations
-  const float* h3l;
+  const float* h3;   // layer-3 activations of the backbone / value tower
   const float* g3;
-  const float* g3l;
   const float* mean;    // [n,act] saved by forward
   const float* mw;
   const float* logstd;
@@ -166,10 +143,8 @@ struct HeadBwdArgs {
   const float* d_logprobs;  // [n,act]
   const float* d_entropy;   // [n,act] or null
   const float* d_values;    // [n,vdim] or null
-  float* dz3;               // [n,256] out: grad wrt backbone layer-3 pre-activation (hi, lo)
-  float* dz3l;
+  float* dz3;               // [n,256] out: grad wrt backbone layer-3 pre-activation
   float* dy3;               // [n,256] out: grad wrt value layer-3 pre-activation (if d_values)
-  float* dy3l;
   float* g_mw;              // [act,256] +=
   float* g_mb;              // [act] +=
   float* g_logstd;          // [act] +=
@@ -218,23 +193,52 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
   for (int c = 0; c < (REG ? 2 : 1); ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) rv[c][j] = 0.f;
-  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < p.n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 h0 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4),
-                           *reinterpret_cast<const float4*>(p.h3l + row * kH + lane * 4));
-    const float4 h1 = add4(*reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4),
-                           *reinterpret_cast<const float4*>(p.h3l + row * kH + 128 + lane * 4));
+  // One warp per row, 152 registers in the REG variant -> 8 warps / SM: without help every row pays a full DRAM
+  // round trip (ncu round 1: 565 us for 1.05 GB).  The row inputs are therefore fetched two rows ahead.
+  struct RowIn {
+    float4 h0, h1, g0, g1;
+    float x, mu, dlp, den, dv0, dv1;
+  };
+  auto load_row = [&](int64_t row) -> RowIn {
+    RowIn r;
+    r.h0 = r.h1 = r.g0 = r.g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.x = r.mu = r.dlp = r.den = r.dv0 = r.dv1 = 0.f;
+    if (row < p.n) {
+      r.h0 = __ldg(reinterpret_cast<const float4*>(p.h3 + row * kH + lane * 4));
+      r.h1 = __ldg(reinterpret_cast<const float4*>(p.h3 + row * kH + 128 + lane * 4));
+      if (has_v) {
+        r.g0 = __ldg(reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4));
+        r.g1 = __ldg(reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4));
+        if (REG) {
+          r.dv0 = __ldg(p.d_values + row * p.vdim);
+          if (p.vdim > 1) r.dv1 = __ldg(p.d_values + row * p.vdim + 1);
+        }
+      }
+      if (lane < p.act) {
+        const int64_t src = p.idx ? p.idx[row] : row;
+        r.x = __ldg(p.action + src * p.act + lane);
+        r.mu = __ldg(p.mean + row * p.act + lane);
+        r.dlp = __ldg(p.d_logprobs + row * p.act + lane);
+        if (p.d_entropy) r.den = __ldg(p.d_entropy + row * p.act + lane);
+      }
+    }
+    return r;
+  };
+  const int64_t row_stride = (int64_t)gridDim.x * nwarp;
+  const int64_t row_first = (int64_t)blockIdx.x * nwarp + warp;
+  const float sd_l = lane < p.act ? expf(p.logstd[lane]) : 1.f;
+  const float var_l = sd_l * sd_l;
+  RowIn nxt0 = load_row(row_first), nxt1 = load_row(row_first + row_stride);
+  for (int64_t row = row_first; row < p.n; row += row_stride) {
+    const RowIn cur = nxt0;
+    nxt0 = nxt1;
+    nxt1 = load_row(row + 2 * row_stride);
+    const float4 h0 = cur.h0, h1 = cur.h1;
     float dmu = 0.f;
     if (lane < p.act) {
-      const int64_t src = p.idx ? p.idx[row] : row;
-      const float x = p.action[src * p.act + lane];
-      const float mu = p.mean[row * p.act + lane];
-      const float sd = expf(p.logstd[lane]);
-      const float var = sd * sd;
-      const float dlp = p.d_logprobs[row * p.act + lane];
-      const float d = x - mu;
-      dmu = dlp * d / var;
-      float dls = dlp * (d * d / var - 1.0f);
-      if (p.d_entropy) dls += p.d_entropy[row * p.act + lane];
+      const float d = cur.x - cur.mu;
+      dmu = cur.dlp * d / var_l;
+      const float dls = cur.dlp * (d * d / var_l - 1.0f) + cur.den;
       atomicAdd(&a_mb[lane], dmu);
       atomicAdd(&a_ls[lane], dls);
     }
@@ -264,21 +268,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
     o0.z = dh0.z * (1.f - h0.z * h0.z); o0.w = dh0.w * (1.f - h0.w * h0.w);
     o1.x = dh1.x * (1.f - h1.x * h1.x); o1.y = dh1.y * (1.f - h1.y * h1.y);
     o1.z = dh1.z * (1.f - h1.z * h1.z); o1.w = dh1.w * (1.f - h1.w * h1.w);
-    store_split(p.dz3, p.dz3l, row * kH + lane * 4, o0);
-    store_split(p.dz3, p.dz3l, row * kH + 128 + lane * 4, o1);
+    *reinterpret_cast<float4*>(p.dz3 + row * kH + lane * 4) = o0;
+    *reinterpret_cast<float4*>(p.dz3 + row * kH + 128 + lane * 4) = o1;
     cb[0] += o0.x; cb[1] += o0.y; cb[2] += o0.z; cb[3] += o0.w;
     cb[4] += o1.x; cb[5] += o1.y; cb[6] += o1.z; cb[7] += o1.w;
 
     if (has_v) {
-      const float4 g0 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + lane * 4),
-                             *reinterpret_cast<const float4*>(p.g3l + row * kH + lane * 4));
-      const float4 g1 = add4(*reinterpret_cast<const float4*>(p.g3 + row * kH + 128 + lane * 4),
-                             *reinterpret_cast<const float4*>(p.g3l + row * kH + 128 + lane * 4));
+      const float4 g0 = cur.g0, g1 = cur.g1;
       float4 dg0 = make_float4(0.f, 0.f, 0.f, 0.f), dg1 = dg0;
 #pragma unroll
       for (int c = 0; c < (REG ? 2 : kMaxVal); ++c) {
         if (c >= p.vdim) break;
-        const float g = p.d_values[row * p.vdim + c];
+        const float g = REG ? (c == 0 ? cur.dv0 : cur.dv1) : p.d_values[row * p.vdim + c];
         const float4 w0 = *reinterpret_cast<const float4*>(s_vw + c * kH + lane * 4);
         const float4 w1 = *reinterpret_cast<const float4*>(s_vw + c * kH + 128 + lane * 4);
         dg0.x += g * w0.x; dg0.y += g * w0.y; dg0.z += g * w0.z; dg0.w += g * w0.w;
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
       q0.z = dg0.z * (1.f - g0.z * g0.z); q0.w = dg0.w * (1.f - g0.w * g0.w);
       q1.x = dg1.x * (1.f - g1.x * g1.x); q1.y = dg1.y * (1.f - g1.y * g1.y);
       q1.z = dg1.z * (1.f - g1.z * g1.z); q1.w = dg1.w * (1.f - g1.w * g1.w);
-      store_split(p.dy3, p.dy3l, row * kH + lane * 4, q0);
-      store_split(p.dy3, p.dy3l, row * kH + 128 + lane * 4, q1);
+      *reinterpret_cast<float4*>(p.dy3 + row * kH + lane * 4) = q0;
+      *reinterpret_cast<float4*>(p.dy3 + row * kH + 128 + lane * 4) = q1;
       cv[0] += q0.x; cv[1] += q0.y; cv[2] += q0.z; cv[3] += q0.w;
       cv[4] += q1.x; cv[5] += q1.y; cv[6] += q1.z; cv[7] += q1.w;
     }
@@ -364,9 +365,9 @@ int head_grid(int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Towers.  Activation / gradient tensors are (hi, lo) pairs: pointer `x` = hi part, `x + n*256` = lo part.
+// Towers.  Activation / gradient tensors are plain fp32 [n,256].
 // ---------------------------------------------------------------------------------------------------------
-struct TowerW {           // fp32 weights (SIMT path, wgrad)
+struct TowerW {           // fp32 weights (SIMT path)
   const float *w0, *b0, *w1, *b1, *w2, *b2;
 };
 struct TowerWS {          // exact-TF32 (hi, lo) copies for the tensor cores (null => SIMT everywhere)
@@ -374,107 +375,80 @@ struct TowerWS {          // exact-TF32 (hi, lo) copies for the tensor cores (nu
   const float *w1th, *w1tl, *w2th, *w2tl;           // transposed [in=256, out=256] (dgrad: dZ . W)
 };
 
-// one hidden layer forward: out(hi,lo) = split(tanh(in . W^T + b))
-int layer_forward(const float* in_hi, const float* in_lo, const int64_t* idx, int64_t n, int in_dim, const float* w,
-                  const float* b, const float* wh, const float* wl, float* out, float* xsplit, cudaStream_t st) {
-  float* out_lo = out + n * kH;
+// one hidden layer forward: out = tanh(in . W^T + b)
+int layer_forward(const float* in, const int64_t* idx, int64_t n, int in_dim, const float* w, const float* b,
+                  const float* wh, const float* wl, float* out, cudaStream_t st) {
   const bool tc_ok = wh != nullptr && idx == nullptr && (in_dim % rb::tc::BK == 0);
   if (tc_ok) {
-    const float *ah = in_hi, *al = in_lo;
-    if (in_lo == nullptr) {  // raw fp32 input (layer 1): split it first
-      int e = rb::tc::split(in_hi, xsplit, xsplit + n * in_dim, n * in_dim, st);
-      if (e) return e;
-      ah = xsplit;
-      al = xsplit + n * in_dim;
-    }
     rb::tc::Params p{};
-    p.M = n; p.K = in_dim; p.bias = b; p.c_hi = out; p.c_lo = out_lo; p.epi = rb::tc::EPI_BIAS_TANH_SPLIT;
-    return rb::tc::launch(ah, al, wh, wl, p, st);
+    p.M = n; p.K = in_dim; p.bias = b; p.c = out; p.epi = rb::tc::EPI_BIAS_TANH;
+    return rb::tc::launch(in, wh, wl, p, st);
   }
   GemmArgs g{};
   g.M = n; g.N = kH; g.ldc = kH; g.k_per_split = 1 << 30;
-  g.A = in_hi; g.A2 = in_lo; g.lda = in_dim; g.a_rows = idx; g.B = w; g.ldb = in_dim; g.K = in_dim; g.bias = b; g.C = out;
-  int e = launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
-  if (e) return e;
-  return rb::tc::split(out, out, out_lo, n * kH, st);  // in place: hi overwrites the fp32 value it was read from
+  g.A = in; g.lda = in_dim; g.a_rows = idx; g.B = w; g.ldb = in_dim; g.K = in_dim; g.bias = b; g.C = out;
+  return launch_gemm<A_KCONTIG, B_KCONTIG, EPI_BIAS_TANH>(g, 1, st);
 }
 
-// X -> H1 -> H2 -> H3 (each [2][n,256])
-int tower_forward(const float* X, const float* Xh, const float* Xl, const int64_t* idx, int64_t n, int in_dim,
-                  const TowerW& w, const TowerWS* ws, float* H1, float* H2, float* H3, float* xsplit, cudaStream_t st) {
-  // Xh/Xl: caller-provided exact-TF32 split of X (cached across epochs), else X is split on the fly into xsplit
-  int e = (Xh && Xl && !idx)
-              ? layer_forward(Xh, Xl, nullptr, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr, ws ? ws->w0l : nullptr,
-                              H1, xsplit, st)
-              : layer_forward(X, nullptr, idx, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr,
-                              ws ? ws->w0l : nullptr, H1, xsplit, st);
+// X -> H1 -> H2 -> H3 (each [n,256])
+int tower_forward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
+                  float* H1, float* H2, float* H3, cudaStream_t st) {
+  int e = layer_forward(X, idx, n, in_dim, w.w0, w.b0, ws ? ws->w0h : nullptr, ws ? ws->w0l : nullptr, H1, st);
   if (e) return e;
-  e = layer_forward(H1, H1 + n * kH, nullptr, n, kH, w.w1, w.b1, ws ? ws->w1h : nullptr, ws ? ws->w1l : nullptr, H2,
-                    xsplit, st);
+  e = layer_forward(H1, nullptr, n, kH, w.w1, w.b1, ws ? ws->w1h : nullptr, ws ? ws->w1l : nullptr, H2, st);
   if (e) return e;
-  return layer_forward(H2, H2 + n * kH, nullptr, n, kH, w.w2, w.b2, ws ? ws->w2h : nullptr, ws ? ws->w2l : nullptr, H3,
-                       xsplit, st);
+  return layer_forward(H2, nullptr, n, kH, w.w2, w.b2, ws ? ws->w2h : nullptr, ws ? ws->w2l : nullptr, H3, st);
 }
 
-// backward through the three hidden layers of one tower, given dZ3 (hi,lo). tmpA/tmpB: [2][n,256] scratch.
-int tower_backward(const float* X, const float* xs_hi, const float* xs_lo, const int64_t* idx, int64_t n, int in_dim,
-                   const TowerW& w,
-                   const TowerWS* ws, const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB,
-                   float* g_w0,
+// backward through the three hidden layers of one tower, given dZ3. tmpA/tmpB: [n,256] scratch.
+int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, const TowerW& w, const TowerWS* ws,
+                   const float* H1, const float* H2, const float* dZ3, float* tmpA, float* tmpB, float* g_w0,
                    float* g_b0, float* g_w1, float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
   const int64_t rows_per_split = 4096;
   const int splits = (int)((n + rows_per_split - 1) / rows_per_split);
   const int64_t cs_rows = 128;
   const int cs_blocks = (int)((n + cs_rows - 1) / cs_rows);
-  const int64_t L = n * kH;  // offset of the lo part
   int e;
-  auto wgrad = [&](const float* dZ, const float* Hin, const float* Hin_lo, const int64_t* in_rows, int in_ld,
-                   float* gw, float* gb, bool need_colsum) -> int {
-    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
-    const int64_t cs_rows_ = cs_rows;
-    if (ws && Hin_lo && !in_rows && (in_ld % rb::tc::BK == 0) && in_ld <= 256) {  // tensor cores (3xTF32)
-      int ee = rb::tc::wgrad(dZ, dZ + L, Hin, Hin_lo, gw, n, in_ld, st);
-      if (ee || !need_colsum) return ee;
-      colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows_);
-      rb::count_launch();
-      cudaError_t ce = cudaPeekAtLastError();
-      return ce == cudaSuccess ? 0 : (int)ce;
-    }
-    // fp32 SIMT, split over samples, atomics
-    GemmArgs g{};
-    g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = Hin; g.B2 = Hin_lo; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw;
-    g.ldc = in_ld; g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
-    int ee = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(g, splits, st);
-    if (ee || !need_colsum) return ee;
-    colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, dZ + L, gb, n, kH, cs_rows);
+  auto colsum = [&](const float* dZ, float* gb) -> int {
+    colsum_kernel<<<cs_blocks, 256, 0, st>>>(dZ, gb, n, kH, cs_rows);
     rb::count_launch();
     cudaError_t ce = cudaPeekAtLastError();
     return ce == cudaSuccess ? 0 : (int)ce;
   };
+  auto wgrad = [&](const float* dZ, const float* Hin, const int64_t* in_rows, int in_ld, float* gw, float* gb,
+                   bool need_colsum) -> int {
+    // gw[256, in_ld] += dZ^T [256, n] . Hin [n, in_ld]
+    int ee;
+    if (ws && !in_rows && (in_ld % rb::tc::BK == 0) && in_ld <= 256) {  // tensor cores (3xTF32)
+      ee = rb::tc::wgrad(dZ, Hin, gw, n, in_ld, st);
+    } else {  // fp32 SIMT, split over samples, atomics
+      GemmArgs g{};
+      g.A = dZ; g.lda = kH; g.B = Hin; g.ldb = in_ld; g.b_rows = in_rows; g.C = gw;
+      g.ldc = in_ld; g.M = kH; g.N = in_ld; g.K = n; g.k_per_split = rows_per_split;
+      ee = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(g, splits, st);
+    }
+    if (ee || !need_colsum) return ee;
+    return colsum(dZ, gb);
+  };
   auto dgrad = [&](const float* dZ, const float* W, const float* Wth, const float* Wtl, const float* Hprev,
                    float* out, float* gb_prev) -> int {
-    // out(hi,lo) = split( (dZ . W) * (1 - Hprev^2) ); the tensor-core epilogue also adds out's column sums to gb_prev
+    // out = (dZ . W) * (1 - Hprev^2); the tensor-core epilogue also adds out's column sums to gb_prev
     if (Wth) {
       rb::tc::Params p{};
-      p.M = n; p.K = kH; p.h_hi = Hprev; p.h_lo = Hprev + L; p.c_hi = out; p.c_lo = out + L; p.colsum = gb_prev;
-      p.epi = rb::tc::EPI_TANHGRAD_SPLIT;
-      return rb::tc::launch(dZ, dZ + L, Wth, Wtl, p, st);
+      p.M = n; p.K = kH; p.h = Hprev; p.c = out; p.colsum = gb_prev; p.epi = rb::tc::EPI_TANHGRAD;
+      return rb::tc::launch(dZ, Wth, Wtl, p, st);
     }
     GemmArgs g{};
-    g.A = dZ; g.A2 = dZ + L; g.lda = kH; g.B = W; g.ldb = kH; g.C = out; g.ldc = kH; g.aux = Hprev; g.aux2 = Hprev + L;
+    g.A = dZ; g.lda = kH; g.B = W; g.ldb = kH; g.C = out; g.ldc = kH; g.aux = Hprev;
     g.ldaux = kH; g.M = n; g.N = kH; g.K = kH; g.k_per_split = 1 << 30;
-    int ee = launch_gemm<A_KCONTIG, B_NCONTIG, EPI_TANHGRAD>(g, 1, st);
-    if (ee) return ee;
-    return rb::tc::split(out, out, out + L, L, st);
+    return launch_gemm<A_KCONTIG, B_NCONTIG, EPI_TANHGRAD>(g, 1, st);
   };
   const bool tc = ws != nullptr;  // tensor-core dgrad adds the bias gradients of layers 2 and 1 in its epilogue
-  if ((e = wgrad(dZ3, H2, H2 + L, nullptr, kH, g_w2, g_b2, false))) return e;  // g_b2: head_bwd_kernel
+  if ((e = wgrad(dZ3, H2, nullptr, kH, g_w2, g_b2, false))) return e;  // g_b2: head_bwd_kernel
   if ((e = dgrad(dZ3, w.w2, ws ? ws->w2th : nullptr, ws ? ws->w2tl : nullptr, H2, tmpA, g_b1))) return e;  // dZ2
-  if ((e = wgrad(tmpA, H1, H1 + L, nullptr, kH, g_w1, g_b1, !tc))) return e;
+  if ((e = wgrad(tmpA, H1, nullptr, kH, g_w1, g_b1, !tc))) return e;
   if ((e = dgrad(tmpA, w.w1, ws ? ws->w1th : nullptr, ws ? ws->w1tl : nullptr, H1, tmpB, g_b0))) return e;  // dZ1
-  if (ws && xs_hi && xs_lo && !idx && in_dim % rb::tc::BK == 0)  // exact-TF32 split of X (from forward / the caller)
-    return wgrad(tmpB, xs_hi, xs_lo, nullptr, in_dim, g_w0, g_b0, !tc);
-  return wgrad(tmpB, X, nullptr, idx, in_dim, g_w0, g_b0, !tc);
+  return wgrad(tmpB, X, idx, in_dim, g_w0, g_b0, !tc);
 }
 
 }  // namespace
@@ -503,13 +477,13 @@ extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_d
   return RB200_OK;
 }
 
-// acts layout (floats): H1 H2 H3 G1 G2 G3, each a (hi, lo) pair of [n,256] | mean [n,act]
-// work layout: 6 gradient pairs of [n,256] | split copy of the input states 2*[n,obs]
-static inline int64_t pair_floats(int64_t n) { return 2 * n * kH; }
+// acts layout (floats): H1 H2 H3 G1 G2 G3, each [n,256] | mean [n,act]
+// work layout: 6 gradient tensors of [n,256]
+static inline int64_t act_floats(int64_t n) { return n * kH; }
 
 extern "C" int64_t rb200_mlp_fwd_scratch_floats(const rb200_mlp_layout* L, int64_t n) {
   if (!L || n <= 0) return 0;
-  return 6 * pair_floats(n) + n * L->act_dim + 2 * n * L->obs_dim + 64;
+  return 6 * act_floats(n) + n * L->act_dim + 64;
 }
 
 // wsplit layout (floats), per tower (value tower first, then backbone), every block 16-byte aligned:
@@ -573,8 +547,7 @@ extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float*
 }
 
 extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                                 const float* states, const float* states_hi, const float* states_lo,
-                                 const float* action, const int64_t* idx, int64_t n,
+                                 const float* states, const float* action, const int64_t* idx, int64_t n,
                                  float* logprobs, float* entropy, float* values, float* acts, float* work,
                                  rb200_stream_t stream) {
   int e = check_layout(L);
@@ -583,21 +556,19 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params,
   if (n <= 0) return RB200_E_SHAPE;
   if (values && L->value_dim == 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  const int64_t PF = pair_floats(n);
+  const int64_t PF = act_floats(n);
   float *H1 = acts, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
   float* mean = G3 + PF;
-  float* xsplit = work + 6 * PF;
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, states_hi, states_lo, idx, n, L->obs_dim, tower_w(L, P, false),
-                         wsplit ? &bws : nullptr, H1, H2, H3, xsplit, st)))
+  if ((e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3, st)))
     return e;
-  if (values && (e = tower_forward(states, states_hi, states_lo, idx, n, L->obs_dim, tower_w(L, P, true),
-                                   wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
+  if (values &&
+      (e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, G3, st)))
     return e;
   HeadFwdArgs h{};
-  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
+  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb;
   h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.sample_mode = 0; h.mean_out = mean;
   h.logprobs = logprobs; h.entropy = entropy; h.values = values; h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
   const size_t smem = sizeof(float) * (size_t)(L->act_dim + L->value_dim) * kH;
@@ -607,8 +578,7 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params,
 }
 
 extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params, const float* wsplit,
-                                  const float* states, const float* states_hi, const float* states_lo,
-                                  const float* action, const int64_t* idx, int64_t n,
+                                  const float* states, const float* action, const int64_t* idx, int64_t n,
                                   const float* d_logprobs, const float* d_entropy, const float* d_values,
                                   const float* acts, float* work, float* grads, rb200_stream_t stream) {
   int e = check_layout(L);
@@ -616,16 +586,16 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   if (!params || !states || !action || !d_logprobs || !acts || !work || !grads) return RB200_E_NULL;
   if (n <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  const int64_t PF = pair_floats(n);
+  const int64_t PF = act_floats(n);
   const float *H1 = acts, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
   const float* mean = G3 + PF;
   float *dZ3 = work, *tA = dZ3 + PF, *tB = tA + PF, *dY3 = tB + PF, *uA = dY3 + PF, *uB = uA + PF;
   const float* P = params;
   float* G = grads;
   HeadBwdArgs h{};
-  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = G3; h.g3l = G3 + n * kH; h.mean = mean; h.mw = P + L->mw;
+  h.h3 = H3; h.g3 = G3; h.mean = mean; h.mw = P + L->mw;
   h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.d_logprobs = d_logprobs;
-  h.d_entropy = d_entropy; h.d_values = d_values; h.dz3 = dZ3; h.dz3l = dZ3 + n * kH; h.dy3 = dY3; h.dy3l = dY3 + n * kH;
+  h.d_entropy = d_entropy; h.d_values = d_values; h.dz3 = dZ3; h.dy3 = dY3;
   h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
   h.g_b2 = G + L->bb2; h.g_vb2 = G + L->vb2;
   h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
@@ -647,21 +617,42 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   }
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  // exact-TF32 split of the input states: the caller's cached copy, else what rb200_mlp_forward left in `work`
-  const float* xs_hi = states_hi ? states_hi : work + 6 * PF;
-  const float* xs_lo = states_lo ? states_lo : work + 6 * PF + n * L->obs_dim;
-  if ((e = tower_backward(states, xs_hi, xs_lo, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2,
+  if ((e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2,
                           dZ3, tA, tB, G + L->bw0, G + L->bb0, G + L->bw1, G + L->bb1, G + L->bw2, G + L->bb2, st)))
     return e;
   if (d_values &&
-      (e = tower_backward(states, xs_hi, xs_lo, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2,
+      (e = tower_backward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2,
                           dY3, uA, uB,
                           G + L->vw0, G + L->vb0, G + L->vw1, G + L->vb1, G + L->vw2, G + L->vb2, st)))
     return e;
   return RB200_OK;
 }
 
-// work: 6 activation pairs + split input copy = rb200_mlp_fwd_scratch_floats(L, n) floats is always enough
+namespace {
+// Rollout-sized batches (a few thousand rows) give each tower GEMM only n/128 CTAs: the actor and the value tower are
+// independent until the head kernel, so they run concurrently on a forked side stream (fork/join with events; legal
+// inside CUDA-graph capture, where it becomes two parallel branches of the graph).
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream& side_stream() {
+  static SideStream ss;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess)
+      ss.ok = true;
+    if (!ss.ok) (void)cudaGetLastError();
+  }
+  return ss;
+}
+}  // namespace
+
+// work: 6 activation tensors; rb200_mlp_fwd_scratch_floats(L, n) floats is always enough
 extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, const float* wsplit,
                                 const float* states, const float* noise, uint64_t seed, uint64_t offset,
                                 const uint64_t* counter_dev, int64_t n, float* action, float* logprobs, float* values,
@@ -671,20 +662,44 @@ extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, 
   if (!params || !states || !action || !logprobs || !work) return RB200_E_NULL;
   if (n <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  const int64_t PF = pair_floats(n);
+  const int64_t PF = act_floats(n);
   float *H1 = work, *H2 = H1 + PF, *H3 = H2 + PF, *G1 = H3 + PF, *G2 = G1 + PF, *G3 = G2 + PF;
-  float* xsplit = G3 + PF;
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, P, false),
-                         wsplit ? &bws : nullptr, H1, H2, H3, xsplit, st)))
+  // few tiles per GEMM -> run the two towers side by side
+  const bool fork = values != nullptr && wsplit != nullptr && n <= (int64_t)64 * rb::sm_count();
+  SideStream* ss = nullptr;
+  if (fork) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(st, &cs);
+    static bool created_outside_capture = false;  // never create streams / events while capturing
+    if (cs == cudaStreamCaptureStatusNone || created_outside_capture) {
+      SideStream& r = side_stream();
+      created_outside_capture = true;
+      if (r.ok) ss = &r;
+    }
+  }
+  if (ss) {
+    cudaError_t ce = cudaEventRecord(ss->fork, st);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ss->s, ss->fork, 0);
+    if (ce != cudaSuccess) return (int)ce;
+    if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true), &vws, G1, G2, G3, ss->s))) return e;
+    ce = cudaEventRecord(ss->join, ss->s);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3,
+                         st)))
     return e;
-  if (values && (e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, P, true),
-                                   wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
+  if (ss) {
+    cudaError_t ce = cudaStreamWaitEvent(st, ss->join, 0);
+    if (ce != cudaSuccess) return (int)ce;
+  } else if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true),
+                                          wsplit ? &vws : nullptr, G1, G2, G3, st))) {
     return e;
+  }
   HeadFwdArgs h{};
-  h.h3 = H3; h.h3l = H3 + n * kH; h.g3 = values ? G3 : nullptr; h.g3l = G3 + n * kH; h.mw = P + L->mw; h.mb = P + L->mb;
+  h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb;
   h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.noise = noise; h.seed = seed; h.offset = offset;
   h.counter = counter_dev; h.sample_mode = 1; h.action_out = action; h.logprobs = logprobs; h.values = values; h.n = n;
   h.act = L->act_dim; h.vdim = L->value_dim;
@@ -696,15 +711,12 @@ extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, 
 
 // value tower + last linear layer only (no bias on the last layer: value_head.py:46)
 namespace {
-__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ g3, const float* __restrict__ g3l,
-                                                         const float* __restrict__ vw3, float* __restrict__ values,
+__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ g3, const float* __restrict__ vw3, float* __restrict__ values,
                                                          int64_t n, int vdim) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < n; row += (int64_t)gridDim.x * nwarp) {
-    const float4 g0 = add4(*reinterpret_cast<const float4*>(g3 + row * kH + lane * 4),
-                           *reinterpret_cast<const float4*>(g3l + row * kH + lane * 4));
-    const float4 g1 = add4(*reinterpret_cast<const float4*>(g3 + row * kH + 128 + lane * 4),
-                           *reinterpret_cast<const float4*>(g3l + row * kH + 128 + lane * 4));
+    const float4 g0 = *reinterpret_cast<const float4*>(g3 + row * kH + lane * 4);
+    const float4 g1 = *reinterpret_cast<const float4*>(g3 + row * kH + 128 + lane * 4);
     for (int c = 0; c < vdim; ++c) {
       const float4 w0 = *reinterpret_cast<const float4*>(vw3 + c * kH + lane * 4);
       const float4 w1 = *reinterpret_cast<const float4*>(vw3 + c * kH + 128 + lane * 4);
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict
 }
 }  // namespace
 
-// work: 3 activation pairs + split input copy
+// work: 3 activation tensors
 extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,
                                const float* states, int64_t n, float* values, float* work, rb200_stream_t stream) {
   int e = check_layout(L);
@@ -725,14 +737,13 @@ extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, c
   if (!params || !states || !values || !work) return RB200_E_NULL;
   if (n <= 0 || L->value_dim <= 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  const int64_t PF = pair_floats(n);
+  const int64_t PF = act_floats(n);
   float *G1 = work, *G2 = G1 + PF, *G3 = G2 + PF;
-  float* xsplit = G3 + PF;
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, nullptr, nullptr, nullptr, n, L->obs_dim, tower_w(L, params, true),
-                         wsplit ? &vws : nullptr, G1, G2, G3, xsplit, st)))
+  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, params, true), wsplit ? &vws : nullptr, G1, G2, G3,
+                         st)))
     return e;
-  value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, G3 + n * kH, params + L->vw3, values, n, L->value_dim);
+  value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, params + L->vw3, values, n, L->value_dim);
   rb::count_launch();
   RB_RETURN_LAUNCH();
 }

@@ -1,17 +1,23 @@
 // K3 tensor-core path: C[M,256] = epilogue( A[M,K] . B[256,K]^T ) on tcgen05 (5th-gen tensor cores), fp32-accurate
 // through 3xTF32 error compensation:   a = a_hi + a_lo, b = b_hi + b_lo (each an exact TF32 number)
 //     a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi        (dropped term a_lo.b_lo ~ 2^-22 relative)
-// Plain TF32/bf16 misses the 1e-4 parity bar of the policy loss, so every operand is stored pre-split (hi, lo) by
-// the producing kernel's epilogue and each k-step issues three kind::tf32 MMAs into the same TMEM accumulator.
+// Plain TF32/bf16 misses the 1e-4 parity bar of the policy loss.  Activations and gradients live in HBM as plain
+// fp32 (one copy): the streamed operand is split into its (hi, lo) pair INSIDE the kernel by transform warps that
+// rewrite the TMA-landed shared-memory tile in place (hi) and into a sibling tile (lo) - the split is elementwise,
+// so it is oblivious to the swizzled tile layout.  (Round-1 v1 stored every activation pre-split: twice the HBM
+// bytes on kernels that were HBM-bound.)  Weights are small and reused by every tile: they stay pre-split.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles, 192 threads):
-//   warp 0   : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B boxes) of A_hi/A_lo [128x32] and B_hi/B_lo [256x32]
+// Structure (one CTA per SM, persistent over 128-row tiles, 320 threads):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B boxes) of A [128x32] and B_hi/B_lo [256x32]
 //                              per k-block into a 2-stage shared-memory ring (96 KB / stage), mbarrier full/empty.
 //   warp 1   : MMA issuer    - one elected thread, tcgen05.mma.cta_group::1.kind::tf32 M=128 N=256 K=8, accumulators
 //                              in TMEM (2 x 256 columns, double-buffered across tiles), tcgen05.commit -> mbarriers.
-//   warps 2-5: epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), bias+tanh or tanh' scaling, hi/lo split,
-//                              transposed through a swizzled shared-memory block so that every global store / load
-//                              instruction covers complete 128-byte row segments; overlaps the next tile's MMAs.
+//   warps 2-5: transform     - A tile -> A_lo tile (the tensor core ignores the low 13 mantissa bits, so the landed
+//                              fp32 tile IS A_hi), fence.proxy.async, arrive on the stage's xf barrier.
+//   warps 6-9: epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), bias+tanh or tanh' scaling, staged in a
+//                              SWIZZLE_128B shared-memory block and written with one TMA tile store per [32 x 32]
+//                              block (per-row global stores cost ~60 issue cycles each, see gae.cu); overlaps the
+//                              next tile's MMAs.
 // Reference op chains replaced: nn.Linear + tanh of MLPPolicy.backbone / ValueHead.mlp
 // (rlinf/models/embodiment/mlp_policy/mlp_policy.py:91-98, modules/value_head.py:37-45) and autograd's dgrad.
 #include "common.cuh"
@@ -24,8 +30,10 @@ namespace tc {
 constexpr int kStages = 2;
 constexpr int kATile = BM * BK * 4;          // 16 KB
 constexpr int kBTile = BN * BK * 4;          // 32 KB
-constexpr int kStageBytes = 2 * kATile + 2 * kBTile;  // A_hi A_lo B_hi B_lo = 96 KB
-constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int kStageBytes = 2 * kATile + 2 * kBTile;  // A(hi) A_lo B_hi B_lo = 96 KB
+constexpr int kXfWarps = 4;                  // transform warps of the forward/dgrad kernel
+constexpr int kThreads = 32 * (2 + kXfWarps + 4);  // producer, MMA, transform, 4 epilogue warps = 320
+constexpr int kStagingBytes = 4 * 2 * 4096;  // epilogue: 4 warps x 2 buffers x [32 rows x 128 B]
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTf32Mask = 0xffffe000u;
 
@@ -95,6 +103,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 struct __align__(16) Barriers {
   uint64_t full[kStages];
+  uint64_t xf[kStages];     // transform warps: the stage's streamed operand has been split into (hi, lo)
   uint64_t empty[kStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
@@ -103,18 +112,39 @@ struct __align__(16) Barriers {
   // forward epilogue: the layer bias (broadcast LDS instead of 64 dependent LDGs / tile);
   // dgrad epilogue: per-CTA column sums of the output tiles (bias gradient), flushed once at kernel end
   float bias[BN];
-  // per-epilogue-warp transpose staging [warp][hi|lo][32 rows][8 float4], 16-byte chunks XOR-swizzled by row & 7
-  float4 stage[4][2][32][8];
 };
 
+__device__ __forceinline__ float4 split_hi4(const float4 x) {
+  return make_float4(__uint_as_float(__float_as_uint(x.x) & kTf32Mask), __uint_as_float(__float_as_uint(x.y) & kTf32Mask),
+                     __uint_as_float(__float_as_uint(x.z) & kTf32Mask), __uint_as_float(__float_as_uint(x.w) & kTf32Mask));
+}
+__device__ __forceinline__ float lo1(float x, float hi) {
+  return __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & kTf32Mask);  // round-to-nearest TF32
+}
+// split of `count` float4 of a TMA-landed tile: dst <- lo (same element positions); src <- hi only when mask_hi
+// (kind::tf32 reads the top 19 bits, so the unmasked fp32 value already acts as hi - tools/tc_flags_probe.py)
+template <int NT>
+__device__ __forceinline__ void transform_tile(float4* __restrict__ src, float4* __restrict__ dst, int count, int t,
+                                               bool mask_hi) {
+#pragma unroll 4
+  for (int i = t; i < count; i += NT) {
+    const float4 x = src[i];
+    const float4 h = split_hi4(x);
+    if (mask_hi) src[i] = h;
+    dst[i] = make_float4(lo1(x.x, h.x), lo1(x.y, h.y), lo1(x.z, h.z), lo1(x.w, h.w));
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, Params p) {
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi,
+                   const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ CUtensorMap tm_c, Params p,
+                   int flags) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; pointer arithmetic (no integer round trip) keeps the shared
   // address space visible to the compiler (LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // 1024-byte aligned: 8 x 4 KB SWIZZLE_128B blocks
+  Barriers* bars = reinterpret_cast<Barriers*>(staging + kStagingBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (p.M + BM - 1) / BM;
@@ -123,6 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->xf[s], kXfWarps);
       tma::mbar_init(&bars->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -135,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
-  if (p.epi == EPI_BIAS_TANH_SPLIT)
+  if (p.epi == EPI_BIAS_TANH)
     for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = p.bias[i];
   else
     for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = 0.f;
@@ -147,24 +178,32 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      tma::prefetch_desc(&tm_a_hi);
-      tma::prefetch_desc(&tm_a_lo);
+      tma::prefetch_desc(&tm_a);
       tma::prefetch_desc(&tm_b_hi);
       tma::prefetch_desc(&tm_b_lo);
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (int)(tile * BM);
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
-          tma::mbar_wait(&bars->empty[s], ph ^ 1u);
-          uint8_t* st = smem + s * kStageBytes;
-          tma::mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
-          tma::load_2d(st, &tm_a_hi, kb * BK, m0, &bars->full[s]);
-          tma::load_2d(st + kATile, &tm_a_lo, kb * BK, m0, &bars->full[s]);
-          tma::load_2d(st + 2 * kATile, &tm_b_hi, kb * BK, 0, &bars->full[s]);
-          tma::load_2d(st + 2 * kATile + kBTile, &tm_b_lo, kb * BK, 0, &bars->full[s]);
-        }
+      // flat loop over this CTA's (tile, k-block) sequence; A boxes are pulled into L2 `pf` k-blocks ahead so that the
+      // real load sees L2 latency: with only two 96 KB stages the DRAM latency would otherwise sit on the critical
+      // path load -> transform -> MMA (measured: 3.2k cycles per k-block against 1.5k of MMA work)
+      const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+      const int64_t total = my_tiles * n_kb;
+      const int pf = (flags >> 8) ? (flags >> 8) & 0xff : 3;
+      for (int64_t j = 0; j < pf && j < total; ++j)
+        tma::prefetch_2d(&tm_a, (int)(j % n_kb) * BK, (int)((blockIdx.x + (j / n_kb) * gridDim.x) * BM));
+      for (int64_t j = 0; j < total; ++j) {
+        const uint32_t it = (uint32_t)j;
+        const int kb = (int)(j % n_kb);
+        const int m0 = (int)((blockIdx.x + (j / n_kb) * gridDim.x) * BM);
+        const int64_t jp = j + pf;
+        if (jp < total && pf < 255)
+          tma::prefetch_2d(&tm_a, (int)(jp % n_kb) * BK, (int)((blockIdx.x + (jp / n_kb) * gridDim.x) * BM));
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+        uint8_t* st = smem + s * kStageBytes;
+        tma::mbar_arrive_expect_tx(&bars->full[s], kATile + 2 * kBTile);
+        tma::load_2d(st, &tm_a, kb * BK, m0, &bars->full[s]);  // rows >= M are zero-filled
+        tma::load_2d(st + 2 * kATile, &tm_b_hi, kb * BK, 0, &bars->full[s]);
+        tma::load_2d(st + 2 * kATile + kBTile, &tm_b_lo, kb * BK, 0, &bars->full[s]);
       }
     }
   } else if (warp == 1) {
@@ -180,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
-          tma::mbar_wait(&bars->full[s], ph);
+          tma::mbar_wait(&bars->full[s], ph);  // B_hi / B_lo have landed
+          tma::mbar_wait(&bars->xf[s], ph);    // A has been split (generic-proxy writes fenced by the writers)
           fence_after_sync();
           const uint32_t sa = tma::smem_u32(smem + s * kStageBytes);
           const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kATile);
@@ -198,9 +238,28 @@ __global__ void __launch_bounds__(kThreads, 1)
         mma_commit(&bars->tmem_full[buf]);  // accumulator complete
       }
     }
+  } else if (warp < 2 + kXfWarps) {
+    // ================= transform warps: A -> (A_hi, A_lo) =================
+    const int t = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        tma::mbar_wait(&bars->full[s], ph);
+        float4* a = reinterpret_cast<float4*>(smem + s * kStageBytes);
+        transform_tile<32 * kXfWarps>(a, a + kATile / 16, kATile / 16, t, (flags & 1) != 0);
+        tma::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+      }
+    }
   } else {
-    // ================= epilogue warps 2..5 =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
+    // ================= epilogue warps 6..9 =================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
+    const int ew = warp - (2 + kXfWarps);  // staging slot
+    float4 (*stg)[32][8] = reinterpret_cast<float4 (*)[32][8]>(staging + ew * 8192);  // [2][32 rows][8 float4]
+    if (lane == 0) tma::prefetch_desc(&tm_c);
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
@@ -208,27 +267,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       tma::mbar_wait(&bars->tmem_full[buf], bph);
       fence_after_sync();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-      float4 (*sh)[8] = bars->stage[warp - 2][0];
-      float4 (*sl)[8] = bars->stage[warp - 2][1];
       const int64_t row0 = tile * BM + q * 32;   // first row of this warp's 32-row slab
       const int rs = lane >> 3, c4 = lane & 7;     // transposed phase: 4 rows x 8 float4 per instruction
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        float4 (*sh)[8] = stg[(c0 >> 5) & 1];
+        // the TMA store issued from this buffer two chunks ago must have finished reading it
+        if (lane == 0) tma::store_wait_read1();
+        __syncwarp();
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);  // asynchronous until tmem_ld_wait
-        if (p.epi == EPI_TANHGRAD_SPLIT) {
-          // previous activation h = hi + lo of this warp's [32 x 32] block: coalesced 128-byte row segments
+        if (p.epi == EPI_TANHGRAD) {
+          // previous activation h of this warp's [32 x 32] block: coalesced 128-byte row segments
           // (4 rows per instruction), transposed through shared memory to one row per thread
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rs;
             const int64_t gr = row0 + rr;
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < p.M) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(p.h_hi + gr * BN + c0) + c4);
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.h_lo + gr * BN + c0) + c4);
-              h = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-            }
+            if (gr < p.M) h = __ldg(reinterpret_cast<const float4*>(p.h + gr * BN + c0) + c4);
             sh[rr][c4 ^ (rr & 7)] = h;
           }
           __syncwarp();
@@ -236,66 +293,52 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float v[4], hi[4], lo[4];
+          float4 v;
           if (p.epi == EPI_STORE) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) hi[e] = __uint_as_float(r[j4 * 4 + e]);
+            v = make_float4(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
+                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+          } else if (p.epi == EPI_BIAS_TANH) {
+            const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j4 * 4]);
+            v.x = tanh_fast(__uint_as_float(r[j4 * 4 + 0]) + b.x);
+            v.y = tanh_fast(__uint_as_float(r[j4 * 4 + 1]) + b.y);
+            v.z = tanh_fast(__uint_as_float(r[j4 * 4 + 2]) + b.z);
+            v.w = tanh_fast(__uint_as_float(r[j4 * 4 + 3]) + b.w);
           } else {
-            if (p.epi == EPI_BIAS_TANH_SPLIT) {
-              const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j4 * 4]);
-              v[0] = tanh_fast(__uint_as_float(r[j4 * 4 + 0]) + b.x);
-              v[1] = tanh_fast(__uint_as_float(r[j4 * 4 + 1]) + b.y);
-              v[2] = tanh_fast(__uint_as_float(r[j4 * 4 + 2]) + b.z);
-              v[3] = tanh_fast(__uint_as_float(r[j4 * 4 + 3]) + b.w);
-            } else {
-              const float4 h = sh[lane][j4 ^ (lane & 7)];  // row `lane` is private to thread `lane` in this phase
-              v[0] = __uint_as_float(r[j4 * 4 + 0]) * (1.0f - h.x * h.x);
-              v[1] = __uint_as_float(r[j4 * 4 + 1]) * (1.0f - h.y * h.y);
-              v[2] = __uint_as_float(r[j4 * 4 + 2]) * (1.0f - h.z * h.z);
-              v[3] = __uint_as_float(r[j4 * 4 + 3]) * (1.0f - h.w * h.w);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
-            sl[lane][j4 ^ (lane & 7)] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            const float4 h = sh[lane][j4 ^ (lane & 7)];  // row `lane` is private to thread `lane` in this phase
+            v.x = __uint_as_float(r[j4 * 4 + 0]) * (1.0f - h.x * h.x);
+            v.y = __uint_as_float(r[j4 * 4 + 1]) * (1.0f - h.y * h.y);
+            v.z = __uint_as_float(r[j4 * 4 + 2]) * (1.0f - h.z * h.z);
+            v.w = __uint_as_float(r[j4 * 4 + 3]) * (1.0f - h.w * h.w);
           }
-          sh[lane][j4 ^ (lane & 7)] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          sh[lane][j4 ^ (lane & 7)] = v;  // == SWIZZLE_128B position of (row lane, 16-byte chunk j4)
         }
+        tma::fence_proxy_async();  // staged tile -> visible to the TMA store
         __syncwarp();
-        if (p.colsum != nullptr && p.epi == EPI_TANHGRAD_SPLIT) {
+        if (lane == 0) {
+          tma::store_2d(&tm_c, &sh[0][0], c0, (int)row0);  // rows >= M are clipped
+          tma::store_commit();
+        }
+        if (p.colsum != nullptr && p.epi == EPI_TANHGRAD) {
           // bias gradient of the layer that produced this tile: column sums over the warp's 32 rows (rows beyond M
-          // hold exact zeros), one vector-free atomic per column per chunk
+          // hold exact zeros: zero-filled A rows and h = 0)
           const int ch = lane >> 2, el = lane & 3;
           float cs = 0.f;
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const float* ph = reinterpret_cast<const float*>(&sh[rr][ch ^ (rr & 7)]);
-            const float* pl = reinterpret_cast<const float*>(&sl[rr][ch ^ (rr & 7)]);
-            cs += ph[el] + pl[el];
-          }
+          for (int rr = 0; rr < 32; ++rr) cs += reinterpret_cast<const float*>(&sh[rr][ch ^ (rr & 7)])[el];
           atomicAdd(&bars->bias[c0 + lane], cs);  // shared-memory atomic (4 warps per address)
         }
-        // transposed stores: every instruction writes 4 complete 128-byte row segments (no partial sectors)
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rs;
-          const int64_t gr = row0 + rr;
-          if (gr < p.M) {
-            reinterpret_cast<float4*>(p.c_hi + gr * BN + c0)[c4] = sh[rr][c4 ^ (rr & 7)];
-            if (p.epi != EPI_STORE) reinterpret_cast<float4*>(p.c_lo + gr * BN + c0)[c4] = sl[rr][c4 ^ (rr & 7)];
-          }
-        }
-        __syncwarp();
       }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(&bars->tmem_empty[buf]);
     }
+    if (lane == 0) tma::store_wait_all();
   }
 
   // ---- teardown ----
   fence_before_sync();
   __syncthreads();
-  if (p.colsum != nullptr && p.epi == EPI_TANHGRAD_SPLIT)
+  if (p.colsum != nullptr && p.epi == EPI_TANHGRAD)
     for (int i = threadIdx.x; i < BN; i += kThreads)
       if (bars->bias[i] != 0.f) atomicAdd(p.colsum + i, bars->bias[i]);
   if (warp == 1) {
@@ -320,11 +363,11 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
          (1ull << 46) | (1ull << 61);
 }
 
-constexpr int kWgradThreads = 192;
+constexpr int kWgXfWarps = 8;                              // transform warps (two operands to split per k-block)
+constexpr int kWgradThreads = 32 * (2 + 4 + kWgXfWarps);  // producer, MMA, 4 epilogue, 8 transform = 448
 __global__ void __launch_bounds__(kWgradThreads, 1)
-    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_z_hi, const __grid_constant__ CUtensorMap tm_z_lo,
-                    const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
-                    float* __restrict__ dW, int64_t n, int IN, int kb_per_chunk) {
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_h,
+                    float* __restrict__ dW, int64_t n, int IN, int kb_per_chunk, int flags) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
@@ -341,6 +384,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->xf[s], kWgXfWarps);
       tma::mbar_init(&bars->empty[s], 1);
     }
     tma::mbar_init(&bars->tmem_full[0], 1);
@@ -357,30 +401,33 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
 
   if (n_kb > 0) {
     if (warp == 0) {
-      // ---- TMA producer: lane 0 arms the barrier, lanes 0..(2*4+2*gB-1) each issue one 4 KB box ----
-      const int n_box = 8 + 2 * gB;
+      // ---- TMA producer: lane 0 arms the barrier, lanes 0..(4+gB-1) each issue one 4 KB box ----
+      const int n_box = 4 + gB;
+      const int pf = (flags >> 8) ? (flags >> 8) & 0xff : 3;  // L2 prefetch distance (k-blocks), see tc_gemm_kernel
+      if (lane < n_box)
+        for (int j = 0; j < pf && j < n_kb; ++j) {
+          if (lane < 4) tma::prefetch_2d(&tm_z, out_tile * 128 + lane * 32, (kb0 + j) * BK);
+          else tma::prefetch_2d(&tm_h, (lane - 4) * 32, (kb0 + j) * BK);
+        }
       for (int it = 0; it < n_kb; ++it) {
+        if (lane < n_box && it + pf < n_kb && pf < 255) {
+          if (lane < 4) tma::prefetch_2d(&tm_z, out_tile * 128 + lane * 32, (kb0 + it + pf) * BK);
+          else tma::prefetch_2d(&tm_h, (lane - 4) * 32, (kb0 + it + pf) * BK);
+        }
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
         if (lane == 0) {
           tma::mbar_wait(&bars->empty[s], ph ^ 1u);
-          tma::mbar_arrive_expect_tx(&bars->full[s], 2 * kATile + 2 * b_bytes);
+          tma::mbar_arrive_expect_tx(&bars->full[s], kATile + b_bytes);
         }
         __syncwarp();
         if (lane < n_box) {
           uint8_t* st = smem + s * kStageBytes;
-          const int m0 = (kb0 + it) * BK;
-          if (lane < 8) {  // A: dZ hi (boxes 0-3), lo (4-7); 32-column group g of this CTA's 128 output rows
-            const int g = lane & 3;
-            tma::load_2d(st + (lane < 4 ? 0 : kATile) + g * 4096, lane < 4 ? &tm_z_hi : &tm_z_lo,
-                         out_tile * 128 + g * 32, m0, &bars->full[s]);
-          } else {         // B: H hi then lo
-            const int j = lane - 8;
-            const bool lo = j >= gB;
-            const int g = lo ? j - gB : j;
-            tma::load_2d(st + 2 * kATile + (lo ? b_bytes : 0) + g * 4096, lo ? &tm_h_lo : &tm_h_hi, g * 32, m0,
-                         &bars->full[s]);
-          }
+          const int m0 = (kb0 + it) * BK;  // samples >= n are zero-filled
+          if (lane < 4)  // A: dZ, 32-column group `lane` of this CTA's 128 output rows
+            tma::load_2d(st + lane * 4096, &tm_z, out_tile * 128 + lane * 32, m0, &bars->full[s]);
+          else           // B: H, 32-column group lane-4
+            tma::load_2d(st + 2 * kATile + (lane - 4) * 4096, &tm_h, (lane - 4) * 32, m0, &bars->full[s]);
         }
       }
     } else if (warp == 1) {
@@ -390,7 +437,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
         for (int it = 0; it < n_kb; ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
-          tma::mbar_wait(&bars->full[s], ph);
+          tma::mbar_wait(&bars->xf[s], ph);  // implies full[s]: the transform warps waited for it
           fence_after_sync();
           const uint32_t sa = tma::smem_u32(smem + s * kStageBytes);
           const uint64_t a_hi = make_desc_mn(sa), a_lo = make_desc_mn(sa + kATile);
@@ -407,7 +454,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
         }
         mma_commit(&bars->tmem_full[0]);
       }
-    } else {
+    } else if (warp < 6) {
       const int q = warp & 3;
       tma::mbar_wait(&bars->tmem_full[0], 0);
       fence_after_sync();
@@ -425,6 +472,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
                                 __uint_as_float(r[j + 3])));
       }
       fence_before_sync();
+    } else {
+      // ---- transform warps: dZ tile and H tile -> (hi in place, lo) ----
+      const int t = threadIdx.x - 6 * 32;
+      const int b_count = (int)(b_bytes / 16);
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        tma::mbar_wait(&bars->full[s], ph);
+        float4* a = reinterpret_cast<float4*>(smem + s * kStageBytes);
+        float4* bsrc = a + 2 * kATile / 16;
+        transform_tile<32 * kWgXfWarps>(a, a + kATile / 16, kATile / 16, t, (flags & 1) != 0);
+        transform_tile<32 * kWgXfWarps>(bsrc, bsrc + b_count, b_count, t, (flags & 1) != 0);
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+      }
     }
   }
   fence_before_sync();
@@ -468,22 +531,23 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
 }
 
 int encode_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int g_debug_flags = 0;
 
-int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, const Params& p,
-           cudaStream_t st) {
+int launch(const float* a, const float* b_hi, const float* b_lo, const Params& p, cudaStream_t st) {
   if (p.K % BK != 0 || p.K <= 0 || p.M <= 0) return RB200_E_SHAPE;
-  const uintptr_t al = reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
-                       reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
-                       reinterpret_cast<uintptr_t>(p.c_hi) | reinterpret_cast<uintptr_t>(p.c_lo);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b_hi) |
+                       reinterpret_cast<uintptr_t>(b_lo) | reinterpret_cast<uintptr_t>(p.c) |
+                       reinterpret_cast<uintptr_t>(p.h);
   if (al & 15) return RB200_E_ALIGN;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  int e = encode_sw128(&ta_hi, a_hi, (uint64_t)p.M, (uint64_t)p.K, BM);
-  if (!e) e = encode_sw128(&ta_lo, a_lo, (uint64_t)p.M, (uint64_t)p.K, BM);
+  CUtensorMap ta, tb_hi, tb_lo, tc;
+  int e = encode_sw128(&ta, a, (uint64_t)p.M, (uint64_t)p.K, BM);
   if (!e) e = encode_sw128(&tb_hi, b_hi, BN, (uint64_t)p.K, BN);
   if (!e) e = encode_sw128(&tb_lo, b_lo, BN, (uint64_t)p.K, BN);
+  if (!e) e = encode_sw128(&tc, p.c, (uint64_t)p.M, BN, 32);  // epilogue store boxes: [32 rows x 32 floats]
   if (e) return RB200_E_UNSUPPORTED;
   static bool attr_done = false;
-  constexpr int kSmem = kStages * kStageBytes + 1024 + (int)sizeof(Barriers);
+  constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
+  static_assert(kSmem <= 232448, "tc_gemm_kernel shared memory");
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
@@ -492,7 +556,7 @@ int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float*
   const int64_t n_tiles = (p.M + BM - 1) / BM;
   const int sms = rb::sm_count();
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  tc_gemm_kernel<<<grid, kThreads, kSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  tc_gemm_kernel<<<grid, kThreads, kSmem, st>>>(ta, tb_hi, tb_lo, tc, p, g_debug_flags);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
@@ -500,18 +564,14 @@ int launch(const float* a_hi, const float* a_lo, const float* b_hi, const float*
 
 int encode_sw128_box32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols);
 
-int wgrad(const float* z_hi, const float* z_lo, const float* h_hi, const float* h_lo, float* dW, int64_t n, int IN,
-          cudaStream_t st) {
+int wgrad(const float* z, const float* h, float* dW, int64_t n, int IN, cudaStream_t st) {
   if (n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
-  const uintptr_t al = reinterpret_cast<uintptr_t>(z_hi) | reinterpret_cast<uintptr_t>(z_lo) |
-                       reinterpret_cast<uintptr_t>(h_hi) | reinterpret_cast<uintptr_t>(h_lo) |
-                       reinterpret_cast<uintptr_t>(dW);
+  const uintptr_t al =
+      reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dW);
   if (al & 15) return RB200_E_ALIGN;
-  CUtensorMap tz_hi, tz_lo, th_hi, th_lo;
-  int e = encode_sw128_box32(&tz_hi, z_hi, (uint64_t)n, 256);
-  if (!e) e = encode_sw128_box32(&tz_lo, z_lo, (uint64_t)n, 256);
-  if (!e) e = encode_sw128_box32(&th_hi, h_hi, (uint64_t)n, (uint64_t)IN);
-  if (!e) e = encode_sw128_box32(&th_lo, h_lo, (uint64_t)n, (uint64_t)IN);
+  CUtensorMap tz, th;
+  int e = encode_sw128_box32(&tz, z, (uint64_t)n, 256);
+  if (!e) e = encode_sw128_box32(&th, h, (uint64_t)n, (uint64_t)IN);
   if (e) return RB200_E_UNSUPPORTED;
   static bool attr_done = false;
   constexpr int kSmem = kStages * kStageBytes + 1024 + (int)sizeof(Barriers);
@@ -525,7 +585,7 @@ int wgrad(const float* z_hi, const float* z_lo, const float* h_hi, const float* 
   if (chunks < 1) chunks = 1;
   if (chunks > n_kb) chunks = n_kb;
   const int kb_per_chunk = (n_kb + chunks - 1) / chunks;
-  tc_wgrad_kernel<<<2 * chunks, kWgradThreads, kSmem, st>>>(tz_hi, tz_lo, th_hi, th_lo, dW, n, IN, kb_per_chunk);
+  tc_wgrad_kernel<<<2 * chunks, kWgradThreads, kSmem, st>>>(tz, th, dW, n, IN, kb_per_chunk, g_debug_flags);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
@@ -552,37 +612,34 @@ int split_transpose(const float* x, float* hi, float* lo, int R, int C, cudaStre
 }  // namespace tc
 }  // namespace rb
 
+// Experiment switches of the tensor-core kernels (see tc_gemm.cuh); not part of the product surface.
+extern "C" int rb200_debug_set_flags(int flags) {
+  rb::tc::g_debug_flags = flags;
+  return RB200_OK;
+}
+
 // Debug / unit-test entry: C[M,256] (fp32) = A[M,K] . B[256,K]^T through the 3xTF32 tensor-core path.
-// `work` holds the split operands: 2*M*K + 2*256*K floats.
+// `work` holds the split weight operand: 2*256*K floats.
 extern "C" int rb200_tc_gemm(const float* A, const float* B, float* C, int64_t M, int K, float* work,
                              rb200_stream_t stream) {
   if (!A || !B || !C || !work) return RB200_E_NULL;
   if (M <= 0 || K <= 0 || K % rb::tc::BK != 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
-  float* a_hi = work;
-  float* a_lo = a_hi + M * K;
-  float* b_hi = a_lo + M * K;
+  float* b_hi = work;
   float* b_lo = b_hi + (int64_t)rb::tc::BN * K;
   int e;
-  if ((e = rb::tc::split(A, a_hi, a_lo, M * K, st))) return e;
   if ((e = rb::tc::split(B, b_hi, b_lo, (int64_t)rb::tc::BN * K, st))) return e;
   rb::tc::Params p{};
-  p.M = M; p.K = K; p.c_hi = C; p.c_lo = C; p.epi = rb::tc::EPI_STORE;
-  return rb::tc::launch(a_hi, a_lo, b_hi, b_lo, p, st);
+  p.M = M; p.K = K; p.c = C; p.epi = rb::tc::EPI_STORE;
+  return rb::tc::launch(A, b_hi, b_lo, p, st);
 }
 
-// Unit-test entry for the weight-gradient GEMM: dW[256, IN] += Z[n,256]^T . H[n,IN]; work = 2*n*(256+IN) floats.
+// Unit-test entry for the weight-gradient GEMM: dW[256, IN] += Z[n,256]^T . H[n,IN]; `work` is unused (kept for
+// ABI stability with the pre-split version).
 extern "C" int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN, float* work,
                               rb200_stream_t stream) {
-  if (!Z || !H || !dW || !work) return RB200_E_NULL;
+  (void)work;
+  if (!Z || !H || !dW) return RB200_E_NULL;
   if (n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
-  cudaStream_t st = rb::as_stream(stream);
-  float* z_hi = work;
-  float* z_lo = z_hi + n * 256;
-  float* h_hi = z_lo + n * 256;
-  float* h_lo = h_hi + n * IN;
-  int e;
-  if ((e = rb::tc::split(Z, z_hi, z_lo, n * 256, st))) return e;
-  if ((e = rb::tc::split(H, h_hi, h_lo, n * IN, st))) return e;
-  return rb::tc::wgrad(z_hi, z_lo, h_hi, h_lo, dW, n, IN, st);
+  return rb::tc::wgrad(Z, H, dW, n, IN, rb::as_stream(stream));
 }

@@ -50,6 +50,12 @@ __device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, 
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// pull a box into L2 ahead of the real load (no shared memory, no completion tracking)
+__device__ __forceinline__ void prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 2-D tiled store smem -> global (bulk async group); OOB parts of the box are clipped
 __device__ __forceinline__ void store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -60,6 +66,8 @@ __device__ __forceinline__ void store_2d(const CUtensorMap* map, const void* sme
 __device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until all committed bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// same, but the most recently committed group may still be in flight (double-buffered staging)
+__device__ __forceinline__ void store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_desc(const CUtensorMap* map) {

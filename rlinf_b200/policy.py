@@ -137,8 +137,7 @@ class MLPPolicy:
             self._scratch[key] = t
         return t
 
-    def forward_train(self, states, action, idx=None, n=None, compute_entropy=True, compute_values=True,
-                      states_split=None):
+    def forward_train(self, states, action, idx=None, n=None, compute_entropy=True, compute_values=True):
         """default_forward (mlp_policy.py:202-236). states/action may be the whole rollout buffer with
         `idx` (int64) selecting this micro-batch's rows.  Keeps activations for `backward`."""
         lib = L.load()
@@ -150,11 +149,10 @@ class MLPPolicy:
         ent = torch.empty_like(logp) if compute_entropy else None
         vals = torch.empty((n, self.value_dim), dtype=torch.float32, device=self.device) if (
             compute_values and self.value_dim > 0) else None
-        sh, sl = states_split if states_split is not None else (None, None)
         L.check(lib.rb200_mlp_forward(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states),
-                                      L.ptr(sh), L.ptr(sl), L.ptr(action), L.ptr(idx), n, L.ptr(logp), L.ptr(ent), L.ptr(vals), L.ptr(acts),
+                                      L.ptr(action), L.ptr(idx), n, L.ptr(logp), L.ptr(ent), L.ptr(vals), L.ptr(acts),
                                       L.ptr(work), L.stream_ptr()), "mlp_forward")
-        self._last = (states, action, idx, n, acts, sh, sl)
+        self._last = (states, action, idx, n, acts)
         out = {"logprobs": logp}
         if ent is not None:
             out["entropy"] = ent
@@ -165,22 +163,12 @@ class MLPPolicy:
     def backward(self, d_logprobs, d_values=None, d_entropy=None):
         """Accumulate (+=) parameter gradients of the last forward_train into `flat_grads`."""
         lib = L.load()
-        states, action, idx, n, acts, sh, sl = self._last
+        states, action, idx, n, acts = self._last
         work = self._buf("work", acts.numel())
         L.check(lib.rb200_mlp_backward(C.byref(self.layout), L.ptr(self.flat_params), self._ws(), L.ptr(states),
-                                       L.ptr(sh), L.ptr(sl), L.ptr(action), L.ptr(idx), n, L.ptr(d_logprobs), L.ptr(d_entropy), L.ptr(d_values),
+                                       L.ptr(action), L.ptr(idx), n, L.ptr(d_logprobs), L.ptr(d_entropy), L.ptr(d_values),
                                        L.ptr(acts), L.ptr(work), L.ptr(self.flat_grads), L.stream_ptr()),
                 "mlp_backward")
-
-    def split_states(self, states):
-        """Exact-TF32 (hi, lo) copy of a [N, obs] observation tensor for the tensor-core GEMMs, or None when the
-        tensor-core path does not apply to layer 1 (obs_dim % 32 != 0)."""
-        if not self.use_tensor_cores or self.obs_dim % 32 != 0:
-            return None
-        hi, lo = torch.empty_like(states), torch.empty_like(states)
-        L.check(L.load().rb200_split_tf32(L.ptr(states), L.ptr(hi), L.ptr(lo), states.numel(), L.stream_ptr()),
-                "split_tf32")
-        return hi, lo
 
     def sample(self, states, noise=None, seed=0, offset=0, calculate_values=True, counter=None, out=None):
         """_generate_actions(mode="train") (mlp_policy.py:256-293): action ~ N(mean, exp(logstd)),

@@ -10,11 +10,10 @@ modes = (True,) if len(sys.argv) > 2 else (True, False)
 for tc in modes:
     pol.use_tensor_cores = tc
     pol.mark_params_changed()
-    ss = pol.split_states(states)
     for _ in range(2):
-        out = pol.forward_train(states, action, compute_entropy=False, states_split=ss); pol.backward(dl, dv, None)
+        out = pol.forward_train(states, action, compute_entropy=False); pol.backward(dl, dv, None)
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    e[0].record(); out = pol.forward_train(states, action, compute_entropy=False, states_split=ss); e[1].record(); pol.backward(dl, dv, None); e[2].record()
+    e[0].record(); out = pol.forward_train(states, action, compute_entropy=False); e[1].record(); pol.backward(dl, dv, None); e[2].record()
     torch.cuda.synchronize()
     print(f"tensor_cores={tc} n={n}: fwd {e[0].elapsed_time(e[1]):.3f} ms  bwd {e[1].elapsed_time(e[2]):.3f} ms", flush=True)
