@@ -70,6 +70,9 @@ class RolloutWorker:
         self.started = False
         self._calls = 0
         self.graph_kernel_count = 0  # kernels replayed per rollout once the CUDA graph exists
+        # V(final_obs) of step t (bootstrap of truncated episodes) only feeds rewards[t]: it runs on a side stream,
+        # concurrently with the policy inference of step t+1 (both are 32-CTA GEMM chains on a 148-SM device)
+        self._side = torch.cuda.Stream(device=policy.device) if policy.device.type == "cuda" else None
 
     def _one_rollout(self, policy_noise=None, env_noise=None):
         """policy_noise [T,B,act] / env_noise [T,B,2*obs+2]: pre-drawn N(0,1)/U(0,1) draws (parity tests);
@@ -79,22 +82,32 @@ class RolloutWorker:
         T, B = buf.T, buf.B
         st = L.stream_ptr()
         pol.mark_params_changed()  # the weight split refresh is always part of the (captured) rollout
+        main, side = torch.cuda.current_stream(), self._side
+        side_busy = False
         for t in range(T):
             # policy/value inference on obs_t -> action, logprob, value rows t  (predict_action_batch)
             pol.sample(buf.states[t], noise=None if policy_noise is None else policy_noise[t], seed=self.seed,
                        offset=0, counter=self.counter, out=(buf.actions[t], buf.prev_logprobs[t], buf.prev_values[t]))
             L.check(lib.rb200_counter_add(L.ptr(self.counter), 1, st), "counter_add")
+            if side_busy:  # V(final_obs) of step t-1 must have read final_obs before this step overwrites it
+                main.wait_stream(side)
+                side_busy = False
             # env.chunk_step: writes obs_{t+1} (row t+1), reward t, flags row t+1
             env.step_into(buf.states[t], buf.actions[t], buf.states[t + 1], buf.final_obs,
                           buf.rewards[t].view(B), buf.terminations[t + 1].view(B), buf.truncations[t + 1].view(B),
                           buf.dones[t + 1].view(B), noise=None if env_noise is None else env_noise[t])
             # compute_bootstrap_rewards (env_worker.py:719-758): r += gamma * V(final_obs) where truncated/done
             if self.auto_reset and pol.value_dim > 0:
-                pol.value(buf.final_obs, out=buf.final_values)
                 flag = buf.truncations[t + 1] if self.bootstrap_type == "standard" else buf.dones[t + 1]
-                L.check(lib.rb200_bootstrap_rewards(L.ptr(buf.rewards[t]), L.ptr(buf.final_values),
-                                                    L.ptr(flag.view(B)), B, pol.value_dim, self.gamma, st),
-                        "bootstrap_rewards")
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    pol.value(buf.final_obs, out=buf.final_values)
+                    L.check(lib.rb200_bootstrap_rewards(L.ptr(buf.rewards[t]), L.ptr(buf.final_values),
+                                                        L.ptr(flag.view(B)), B, pol.value_dim, self.gamma,
+                                                        L.stream_ptr()), "bootstrap_rewards")
+                side_busy = True
+        if side_busy:
+            main.wait_stream(side)
         # final extra inference for the bootstrap value row T (env_worker.py:1237-1306)
         if pol.value_dim > 0:
             pol.value(buf.states[T], out=buf.prev_values[T])
