@@ -260,6 +260,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int ew = warp - (2 + kXfWarps);  // staging slot
     float4 (*stg)[32][8] = reinterpret_cast<float4 (*)[32][8]>(staging + ew * 8192);  // [2][32 rows][8 float4]
     if (lane == 0) tma::prefetch_desc(&tm_c);
+    const int rs = lane >> 3, c4 = lane & 7;  // transposed phase: 4 rows x 8 float4 per instruction
+    // EPI_TANHGRAD: the previous activation h of the NEXT [32 x 32] block is fetched into registers while the
+    // current block is processed (ncu round 1: with the loads issued per block the dgrad epilogue exposed one DRAM
+    // round trip per block and ran at 248 us against 173 us for the forward GEMM of the same shape)
+    float4 hp[8];
+    auto load_h = [&](int64_t r0, int cc) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t gr = r0 + it * 4 + rs;
+        hp[it] = gr < p.M ? __ldg(reinterpret_cast<const float4*>(p.h + gr * BN + cc) + c4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (p.epi == EPI_TANHGRAD && (int64_t)blockIdx.x < n_tiles) load_h((int64_t)blockIdx.x * BM + q * 32, 0);
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
@@ -268,7 +282,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       fence_after_sync();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
       const int64_t row0 = tile * BM + q * 32;   // first row of this warp's 32-row slab
-      const int rs = lane >> 3, c4 = lane & 7;     // transposed phase: 4 rows x 8 float4 per instruction
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float4 (*sh)[8] = stg[(c0 >> 5) & 1];
@@ -278,17 +291,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);  // asynchronous until tmem_ld_wait
         if (p.epi == EPI_TANHGRAD) {
-          // previous activation h of this warp's [32 x 32] block: coalesced 128-byte row segments
-          // (4 rows per instruction), transposed through shared memory to one row per thread
+          // h block (coalesced 128-byte row segments, 4 rows per instruction) -> shared memory, one row per thread
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rs;
-            const int64_t gr = row0 + rr;
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < p.M) h = __ldg(reinterpret_cast<const float4*>(p.h + gr * BN + c0) + c4);
-            sh[rr][c4 ^ (rr & 7)] = h;
+            sh[rr][c4 ^ (rr & 7)] = hp[it];
           }
           __syncwarp();
+          if (c0 + 32 < BN) load_h(row0, c0 + 32);
+          else if (tile + gridDim.x < n_tiles) load_h((tile + gridDim.x) * BM + q * 32, 0);
         }
         tmem_ld_wait();
 #pragma unroll
