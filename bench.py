@@ -172,6 +172,15 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_ncu_mlp_step_v3_table.txt, profiles/r01_ncu_gae_v4_summary.txt); only valid at the captured shape.
+NCU_TRAFFIC = {
+    ("tc_gemm_fwd", 262144): 485.4e6,   # 269.1 MB read + 216.3 MB written back before the kernel ends (rest stays in L2)
+    ("tc_wgrad", 262144): 541.6e6,
+    ("gae_scan", 512, 4096): 18.9e6,    # reads only: the 16.8 MB of results are still in L2 when the kernel ends
+}
+
+
 def kernel_rooflines(a, peaks, torch):
     """Live CUDA-event timing of the HBM-bound kernels at the workload's shapes. Each kernel is launched
     from a captured CUDA graph over ROT independent input sets whose total size exceeds L2 (126 MB), so
@@ -222,7 +231,8 @@ def kernel_rooflines(a, peaks, torch):
 
     t = time_graph(gae_all, rot)
     out["gae_scan"] = {"bound": "hbm", "achieved": bytes_gae / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": bytes_gae / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": t * 1e6,
+                       "frac": bytes_gae / t / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get(("gae_scan", T, B)),
+                       "us_per_launch": t * 1e6,
                        "algorithmic_bytes": bytes_gae, "launch_note": "includes the 48-byte stats memset node"}
     del sets
 
@@ -276,7 +286,8 @@ def kernel_rooflines(a, peaks, torch):
         t = time_graph(fn, reps_k)
         out[key] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": flops / t / 1e12 / peaks["bf16_tflops"], "frac_of_3xtf32_ceiling": flops / t / 1e12 / ceiling,
-                    "traffic": None, "us_per_launch": t * 1e6, "algorithmic_flops": flops,
+                    "traffic": NCU_TRAFFIC.get((key, n)), "us_per_launch": t * 1e6, "algorithmic_flops": flops,
+                    "algorithmic_bytes": n * K * 4 + n * 256 * 4 if key == "tc_gemm_fwd" else n * K * 4 + n * 256 * 4,
                     "hbm_gbs": (n * K * 4 + n * 256 * 4) / t / 1e9, "rows": n, "note": note}
     return out
 
@@ -443,7 +454,8 @@ def run_ours(a):
                     "kernel": "rb::tc::tc_gemm_kernel (tcgen05 kind::tf32, 3xTF32-compensated fp32 GEMM of the MLP towers; "
                               "forward/dgrad), mini-batch shape",
                     "bound": "tensor", "achieved": g["achieved"], "peak": g["peak"], "unit": "TFLOP/s", "frac": g["frac"],
-                    "traffic": None, "frac_of_3xtf32_ceiling": g["frac_of_3xtf32_ceiling"],
+                    "traffic": g["traffic"], "algorithmic_bytes": g["algorithmic_bytes"],
+                    "frac_of_3xtf32_ceiling": g["frac_of_3xtf32_ceiling"],
                     "us_per_launch": g["us_per_launch"], "algorithmic_flops": g["algorithmic_flops"],
                     "hbm_gbs": g["hbm_gbs"],
                     "note": "achieved = logical fp32 flops (2*n*256*256) / live CUDA-event time per launch; peak = measured "
