@@ -48,6 +48,8 @@ def parse():
                     help="envs in the bounded CPU sample (0 = 512 for cpu_baseline, 256 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-bench", action="store_true")
+    ap.add_argument("--rollout", default="auto", choices=["auto", "fused", "graph"],
+                    help="rollout implementation: persistent fused kernel, per-kernel CUDA graph, or the library default")
     return ap.parse_args()
 
 
@@ -309,8 +311,9 @@ def run_ours(a):
 
     lib = L.load()
     peaks = measured_peaks()
+    over = {} if a.rollout == "auto" else {"rollout.fused_kernel": a.rollout == "fused"}
     cfg = synthetic_ppo_config(B=a.B, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
-                               num_minibatches=a.minibatches, world_size=world)
+                               num_minibatches=a.minibatches, world_size=world, **over)
     run = EmbodiedRunner(cfg)
     n_env_steps = a.B * a.T
 

@@ -273,6 +273,28 @@ int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN,
  * hi part in shared memory (not needed: the tensor core truncates), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
 int rb200_debug_set_flags(int flags);
 
+/* Persistent fused rollout (csrc/rollout_fused.cu): the whole T-step loop of one rank - MLP actor/critic inference,
+ * Normal sampling, synthetic-env dynamics with auto-reset and the truncation bootstrap of rewards - in ONE kernel;
+ * CTA c owns environments [c*E, c*E+E) for all T steps.  Replaces EnvWorker.interact / MultiStepRolloutWorker.generate
+ * (rlinf/workers/env/env_worker.py:1059-1349, rlinf/workers/rollout/hf/huggingface_worker.py:678-781) for the
+ * MLP-policy + device-resident env case; same buffers, row alignment and random streams as the per-kernel path
+ * (rb200_mlp_sample + rb200_synth_env_step + rb200_mlp_value + rb200_bootstrap_rewards per step).
+ * rb200_rollout_fused_supported() == 0 iff hidden == 256, obs_dim % 4 == 0, obs_dim <= 256, value_dim <= 1 and
+ * B <= 32 * #SM.  `wt` (rb200_rollout_fused_wt_floats floats) holds the transposed hidden weights; refresh it with
+ * rb200_rollout_fused_prepare() after every parameter update.  states row 0 is the current observation (input);
+ * the device counters are read once (step t uses counter + t): add T to both afterwards (rb200_counter_add). */
+int64_t rb200_rollout_fused_wt_floats(const rb200_mlp_layout* L);
+int rb200_rollout_fused_supported(const rb200_mlp_layout* L, int B);
+int rb200_rollout_fused_prepare(const rb200_mlp_layout* L, const float* params, float* wt, rb200_stream_t stream);
+int rb200_rollout_fused(const rb200_mlp_layout* L, const float* params, const float* wt, const float* w_s,
+                        const float* w_a, float* states, float* actions, float* logprobs, float* values,
+                        float* rewards, uint8_t* terminations, uint8_t* truncations, uint8_t* dones,
+                        float* final_obs, float* final_values, int32_t* elapsed, const float* policy_noise,
+                        const float* env_noise, const uint64_t* counter_policy, const uint64_t* counter_env,
+                        uint64_t seed_policy, uint64_t seed_env, uint64_t offset_policy, int T, int B,
+                        int max_episode_steps, int auto_reset, int bootstrap_on_done, double gamma, double p_term,
+                        double noise_std, double reward_noise_std, rb200_stream_t stream);
+
 /* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
  * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */
 int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,

@@ -12,11 +12,15 @@ are written by the kernels directly into one `[T(+1), B, ...]` buffer in HBM - t
 Row alignment (env_worker.py:1120-1202): row t holds the action/logprob/value computed from obs_t,
 `dones[t]` = done flags produced by step t-1 (row 0 all False), `rewards[t]` = reward of step t with the
 truncation bootstrap gamma*V(final_obs) already folded in.
-The whole loop is captured once in a CUDA graph (rollout.enable_cuda_graph) and replayed.
+Two implementations of the same loop: the persistent fused kernel (`rb200_rollout_fused`, one launch per rollout,
+default whenever it supports the problem; `rollout.fused_kernel: false` disables it) and the per-kernel loop
+captured once in a CUDA graph (rollout.enable_cuda_graph) and replayed - any env exposing `step_into` works there.
 """
 from __future__ import annotations
 
 import torch
+
+import ctypes as C
 
 from . import _lib as L
 
@@ -58,6 +62,8 @@ class RolloutBuffer:
 class RolloutWorker:
     """One rank's env + policy replica."""
 
+    FUSED_AUTO_MAX_ENVS_PER_CTA = 16
+
     def __init__(self, cfg, policy, env, buffer: RolloutBuffer):
         self.cfg, self.policy, self.env, self.buf = cfg, policy, env, buffer
         self.gamma = float(cfg.algorithm.get("gamma", 1))
@@ -73,10 +79,47 @@ class RolloutWorker:
         # V(final_obs) of step t (bootstrap of truncated episodes) only feeds rewards[t]: it runs on a side stream,
         # concurrently with the policy inference of step t+1 (both are 32-CTA GEMM chains on a 148-SM device)
         self._side = torch.cuda.Stream(device=policy.device) if policy.device.type == "cuda" else None
+        # persistent fused kernel: needs the synthetic env's dynamics (w_s, w_a) and a supported MLP shape
+        mode = cfg.rollout.get("fused_kernel", "auto")  # True / False / "auto"
+        supported = (policy.device.type == "cuda" and hasattr(env, "w_s") and hasattr(env, "w_a")
+                     and L.load().rb200_rollout_fused_supported(C.byref(policy.layout), int(buffer.B)) == 0)
+        if mode == "auto":
+            # measured (round 1, T = 512, ms per rollout fused / per-kernel graph): B = 512: 23 / 53, 1024: 33 / 55,
+            # 2048: 46 / 55, 4096: 88 / 54 - the fused kernel wins while a CTA owns <= 16 environments (small per-rank
+            # batches, where the per-kernel loop is launch-latency bound); at E = 28 its shared-memory-broadcast SIMT
+            # layers lose to the tensor-core GEMM chain
+            sms = torch.cuda.get_device_properties(policy.device).multi_processor_count
+            mode = -(-int(buffer.B) // sms) <= self.FUSED_AUTO_MAX_ENVS_PER_CTA
+        self._fused = bool(mode) and supported
+
+    def _fused_rollout(self, policy_noise=None, env_noise=None):
+        """The whole T-step loop in one persistent kernel (csrc/rollout_fused.cu)."""
+        lib = L.load()
+        buf, pol, env = self.buf, self.policy, self.env
+        st = L.stream_ptr()
+        lay = C.byref(pol.layout)
+        wt = pol._buf("rollout_wt", lib.rb200_rollout_fused_wt_floats(lay))
+        L.check(lib.rb200_rollout_fused_prepare(lay, L.ptr(pol.flat_params), L.ptr(wt), st), "rollout_fused_prepare")
+        L.check(lib.rb200_rollout_fused(
+            lay, L.ptr(pol.flat_params), L.ptr(wt), L.ptr(env.w_s), L.ptr(env.w_a), L.ptr(buf.states),
+            L.ptr(buf.actions), L.ptr(buf.prev_logprobs), L.ptr(buf.prev_values) if pol.value_dim > 0 else None,
+            L.ptr(buf.rewards), L.ptr(buf.terminations), L.ptr(buf.truncations), L.ptr(buf.dones),
+            L.ptr(buf.final_obs), L.ptr(buf.final_values) if pol.value_dim > 0 else None, L.ptr(env.elapsed),
+            L.ptr(policy_noise), L.ptr(env_noise), L.ptr(self.counter), L.ptr(env.counter), self.seed, env.seed, 0,
+            buf.T, buf.B, env.max_episode_steps, int(self.auto_reset), int(self.bootstrap_type != "standard"),
+            self.gamma, env.p_term, env.noise_std, env.reward_noise_std, st), "rollout_fused")
+        L.check(lib.rb200_counter_add(L.ptr(self.counter), buf.T, st), "counter_add")
+        L.check(lib.rb200_counter_add(L.ptr(env.counter), buf.T, st), "counter_add")
 
     def _one_rollout(self, policy_noise=None, env_noise=None):
         """policy_noise [T,B,act] / env_noise [T,B,2*obs+2]: pre-drawn N(0,1)/U(0,1) draws (parity tests);
         None -> Philox on the device."""
+        if self._fused:
+            if policy_noise is not None:
+                policy_noise = policy_noise.contiguous()
+            if env_noise is not None:
+                env_noise = env_noise.contiguous()
+            return self._fused_rollout(policy_noise, env_noise)
         lib = L.load()
         buf, pol, env = self.buf, self.policy, self.env
         T, B = buf.T, buf.B
@@ -122,7 +165,7 @@ class RolloutWorker:
         else:
             buf.states[0].copy_(buf.states[buf.T])  # last obs of the previous rollout (bootstrap_step)
         # dones row 0 = zeros (env_worker.py:899-945): never written by the loop, stays zero
-        if not self._use_graph or self._calls == 0:
+        if self._fused or not self._use_graph or self._calls == 0:
             self._one_rollout()  # first call runs eagerly (also allocates every scratch buffer)
             self._calls += 1
             return

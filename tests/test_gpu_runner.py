@@ -75,6 +75,77 @@ def test_rollout_buffer_alignment_vs_oracle(bootstrap_type):
     torch.testing.assert_close(b["forward_inputs"]["action"], ob["forward_inputs"]["action"], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("bootstrap_type", ["always", "standard"])
+def test_fused_rollout_kernel_vs_oracle(bootstrap_type):
+    """The persistent fused rollout kernel (rb200_rollout_fused) fills the same buffer rows as the reference's
+    loop for the same injected noise: flags bit-exact, floats within 1e-4."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    B, T, obs, act = 64, 24, 8, 2
+    cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, **{"algorithm.bootstrap_type": bootstrap_type,
+                                                                          "env.train.p_term": 0.05,
+                                                                          "env.train.max_episode_steps": 10})
+    run = EmbodiedRunner(cfg)
+    assert run.rollout._fused
+    orc = RunnerOracle(cfg, params={n: p.detach().cpu().clone() for n, p in run.actor.model.named_parameters()})
+    g = torch.Generator().manual_seed(5)
+    pn = torch.randn(T + 1, B, act, generator=g)
+    en = torch.cat([torch.randn(T, B, obs + 1, generator=g), torch.rand(T, B, 1, generator=g),
+                    torch.randn(T, B, obs, generator=g)], -1)
+    s0 = torch.randn(B, obs, generator=g)
+    orc.env.state = s0.clone()
+    orc.obs = {"states": orc.env.state}
+    ob = orc.rollout(policy_noise=pn, env_noise=en)
+    run.rollout.started = True
+    run.buffer.states[0].copy_(s0)
+    run.rollout._one_rollout(policy_noise=pn[:T].cuda(), env_noise=en.cuda())
+    b = _cpu_batch(run.buffer.as_batch())
+    for k in ("dones", "terminations", "truncations"):
+        assert torch.equal(b[k], ob[k]), k
+    assert bool(ob["truncations"].any()) and bool(ob["terminations"].any())
+    for k in ("rewards", "prev_values", "prev_logprobs"):
+        torch.testing.assert_close(b[k], ob[k], rtol=1e-4, atol=2e-5, msg=k)
+    torch.testing.assert_close(b["forward_inputs"]["states"], ob["forward_inputs"]["states"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["forward_inputs"]["action"], ob["forward_inputs"]["action"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("B", [300, 1000, 2000, 4096])
+def test_fused_rollout_matches_per_kernel_path(B):
+    """Device RNG: the fused kernel and the per-kernel CUDA-graph loop consume the same Philox streams, so two
+    consecutive rollouts agree (flags exactly, floats up to fp32 summation order). Covers E = 3, 7, 14, 28
+    environments per CTA (all four template instances)."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    T, obs, act = 6, 8, 3
+    bufs = []
+    for fused in (True, False):
+        cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, **{"rollout.fused_kernel": fused,
+                                                                              "env.train.p_term": 0.03,
+                                                                              "env.train.max_episode_steps": 5,
+                                                                              "algorithm.bootstrap_type": "always"})
+        run = EmbodiedRunner(cfg)
+        assert run.rollout._fused == fused
+        out = []
+        for _ in range(3):  # eager, graph capture, graph replay on the per-kernel path
+            run.rollout_phase()
+            torch.cuda.synchronize()
+            out.append(_cpu_batch(run.buffer.as_batch()))
+            out[-1]["elapsed"] = run.env.elapsed.cpu().clone()
+        bufs.append(out)
+    for r in range(3):
+        a, b = bufs[0][r], bufs[1][r]
+        for k in ("dones", "terminations", "truncations"):
+            assert torch.equal(a[k], b[k]), (r, k)
+        assert torch.equal(a["elapsed"], b["elapsed"]), r
+        for k in ("rewards", "prev_values", "prev_logprobs"):
+            torch.testing.assert_close(a[k], b[k], rtol=2e-3, atol=2e-4, msg=f"{r} {k}")
+        torch.testing.assert_close(a["forward_inputs"]["states"], b["forward_inputs"]["states"], rtol=2e-3, atol=2e-4)
+        torch.testing.assert_close(a["forward_inputs"]["action"], b["forward_inputs"]["action"], rtol=2e-3, atol=2e-4)
+    assert bool(bufs[0][2]["dones"].any())
+
+
 @pytest.mark.parametrize("accum", [1, 2])
 def test_update_matches_oracle_after_k_steps(accum):
     """Same rollout batch -> advantages -> shuffled mini/micro-batches -> k optimiser steps: parameters,
@@ -119,7 +190,8 @@ def test_full_iterations_with_cuda_graph_rollout():
     from rlinf_b200.config import synthetic_ppo_config
     from rlinf_b200.runner import EmbodiedRunner
 
-    cfg = synthetic_ppo_config(B=256, T=16, obs_dim=8, action_dim=2, update_epoch=2, num_minibatches=2)
+    cfg = synthetic_ppo_config(B=256, T=16, obs_dim=8, action_dim=2, update_epoch=2, num_minibatches=2,
+                               **{"rollout.fused_kernel": False})
     run = EmbodiedRunner(cfg)
     ms, acts = [], []
     for _ in range(3):
