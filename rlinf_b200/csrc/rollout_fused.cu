@@ -93,17 +93,69 @@ __device__ __forceinline__ void layer(const float* __restrict__ in_s, int K, con
   for (int e = 0; e < EMAX; ++e) out_s[e * kH + j] = tanh_fast(acc[e] + b);
 }
 
+// Register-tiled variant for many environments per CTA: thread = 4 consecutive columns x EMAX/4 environments
+// (64 column groups x 4 environment groups), so one broadcast LDS.128 feeds 16 FMAs instead of 4 and the weight rows
+// are read as LDG.128.  Same k-ascending fmaf order per output as layer<>: bit-identical results.
+template <int EMAX>
+__device__ __forceinline__ void layer_tiled(const float* __restrict__ in_s, int K, const float* __restrict__ Wt,
+                                            const float* __restrict__ bias, float* __restrict__ out_s, int tid) {
+  constexpr int ET = EMAX / 4;
+  const int cg = tid & 63, eg = tid >> 6;
+  const float* in_e = in_s + (size_t)eg * ET * K;
+  const float4* W4 = reinterpret_cast<const float4*>(Wt) + cg;  // row k starts at W4[k * 64]
+  float4 acc[ET];
+#pragma unroll
+  for (int e = 0; e < ET; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w0 = __ldg(W4), w1 = __ldg(W4 + 64), w2 = __ldg(W4 + 128), w3 = __ldg(W4 + 192);
+  for (int k = 0; k < K; k += 4) {
+    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;
+    if (k + 4 < K) {
+      n0 = __ldg(W4 + (size_t)(k + 4) * 64);
+      n1 = __ldg(W4 + (size_t)(k + 5) * 64);
+      n2 = __ldg(W4 + (size_t)(k + 6) * 64);
+      n3 = __ldg(W4 + (size_t)(k + 7) * 64);
+    }
+#pragma unroll
+    for (int e = 0; e < ET; ++e) {
+      const float4 xv = *reinterpret_cast<const float4*>(in_e + e * K + k);
+      acc[e].x = fmaf(xv.x, w0.x, acc[e].x); acc[e].y = fmaf(xv.x, w0.y, acc[e].y);
+      acc[e].z = fmaf(xv.x, w0.z, acc[e].z); acc[e].w = fmaf(xv.x, w0.w, acc[e].w);
+      acc[e].x = fmaf(xv.y, w1.x, acc[e].x); acc[e].y = fmaf(xv.y, w1.y, acc[e].y);
+      acc[e].z = fmaf(xv.y, w1.z, acc[e].z); acc[e].w = fmaf(xv.y, w1.w, acc[e].w);
+      acc[e].x = fmaf(xv.z, w2.x, acc[e].x); acc[e].y = fmaf(xv.z, w2.y, acc[e].y);
+      acc[e].z = fmaf(xv.z, w2.z, acc[e].z); acc[e].w = fmaf(xv.z, w2.w, acc[e].w);
+      acc[e].x = fmaf(xv.w, w3.x, acc[e].x); acc[e].y = fmaf(xv.w, w3.y, acc[e].y);
+      acc[e].z = fmaf(xv.w, w3.z, acc[e].z); acc[e].w = fmaf(xv.w, w3.w, acc[e].w);
+    }
+    w0 = n0; w1 = n1; w2 = n2; w3 = n3;
+  }
+  const float4 b = *reinterpret_cast<const float4*>(bias + 4 * cg);
+#pragma unroll
+  for (int e = 0; e < ET; ++e)
+    *reinterpret_cast<float4*>(out_s + (size_t)(eg * ET + e) * kH + 4 * cg) =
+        make_float4(tanh_fast(acc[e].x + b.x), tanh_fast(acc[e].y + b.y), tanh_fast(acc[e].z + b.z),
+                    tanh_fast(acc[e].w + b.w));
+}
+
+// EMAX == 32 (up to 32 environments per CTA) uses the register-tiled layer, smaller slices the column-per-thread one
+template <int EMAX>
+__device__ __forceinline__ void layer_any(const float* __restrict__ in_s, int K, const float* __restrict__ Wt,
+                                          const float* __restrict__ bias, float* __restrict__ out_s, int j) {
+  if constexpr (EMAX >= 32) layer_tiled<EMAX>(in_s, K, Wt, bias, out_s, j);
+  else layer<EMAX>(in_s, K, Wt, bias, out_s, j);
+}
+
 // value tower on in_s -> g3 in bufB (uses bufC as the middle buffer); every thread must call it
 template <int EMAX>
 __device__ __forceinline__ void value_tower(const FusedArgs& p, const float* in_s, float* bufB, float* bufC, int j) {
   const float* P = p.params;
   const float* wt_v = p.wt;  // value tower first
   const size_t n0 = (size_t)p.obs * kH, nn = (size_t)kH * kH;
-  layer<EMAX>(in_s, p.obs, wt_v, P + p.L.vb0, bufB, j);
+  layer_any<EMAX>(in_s, p.obs, wt_v, P + p.L.vb0, bufB, j);
   __syncthreads();
-  layer<EMAX>(bufB, kH, wt_v + n0, P + p.L.vb1, bufC, j);
+  layer_any<EMAX>(bufB, kH, wt_v + n0, P + p.L.vb1, bufC, j);
   __syncthreads();
-  layer<EMAX>(bufC, kH, wt_v + n0 + nn, P + p.L.vb2, bufB, j);
+  layer_any<EMAX>(bufC, kH, wt_v + n0 + nn, P + p.L.vb2, bufB, j);
   __syncthreads();
 }
 
@@ -161,11 +213,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fused_kernel(FusedArgs p)
 
   for (int t = 0; t < T; ++t) {
     // ---- actor tower: x -> bufA -> bufB -> bufA (h3) ----
-    layer<EMAX>(x, obs, wt_b, P + p.L.bb0, bufA, j);
+    layer_any<EMAX>(x, obs, wt_b, P + p.L.bb0, bufA, j);
     __syncthreads();
-    layer<EMAX>(bufA, kH, wt_b + n0, P + p.L.bb1, bufB, j);
+    layer_any<EMAX>(bufA, kH, wt_b + n0, P + p.L.bb1, bufB, j);
     __syncthreads();
-    layer<EMAX>(bufB, kH, wt_b + n0 + nn, P + p.L.bb2, bufA, j);
+    layer_any<EMAX>(bufB, kH, wt_b + n0 + nn, P + p.L.bb2, bufA, j);
     __syncthreads();
     // ---- value tower: x -> bufB -> bufC -> bufB (g3) ----
     if (has_v) value_tower<EMAX>(p, x, bufB, bufC, j);

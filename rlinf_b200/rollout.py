@@ -85,9 +85,9 @@ class RolloutWorker:
                      and L.load().rb200_rollout_fused_supported(C.byref(policy.layout), int(buffer.B)) == 0)
         if mode == "auto":
             # measured (round 1, T = 512, ms per rollout fused / per-kernel graph): B = 512: 23 / 53, 1024: 33 / 55,
-            # 2048: 46 / 55, 4096: 88 / 54 - the fused kernel wins while a CTA owns <= 16 environments (small per-rank
-            # batches, where the per-kernel loop is launch-latency bound); at E = 28 its shared-memory-broadcast SIMT
-            # layers lose to the tensor-core GEMM chain
+            # 2048: 46 / 55, 4096: 71 / 54 (88 before the register-tiled layer) - the fused kernel wins while a CTA owns <= 16 environments (small per-rank
+            # batches, where the per-kernel loop is launch-latency bound); at E = 28 its fp32 SIMT layers (weight-load latency with only
+            # 8 warps / SM) still lose to the tensor-core GEMM chain
             sms = torch.cuda.get_device_properties(policy.device).multi_processor_count
             mode = -(-int(buffer.B) // sms) <= self.FUSED_AUTO_MAX_ENVS_PER_CTA
         self._fused = bool(mode) and supported
