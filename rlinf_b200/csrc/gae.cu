@@ -20,17 +20,7 @@
 
 namespace {
 
-constexpr int kR = 16;  // timesteps per stage
-constexpr int kS = 8;   // pipeline stages
 constexpr int kW = 32;  // trajectories (columns) per CTA = one warp
-
-struct __align__(128) Stage {
-  float r[kR][kW];
-  float v[kR][kW];
-  uint8_t d[kR][kW];
-  uint8_t m[kR][kW];
-};
-static_assert(sizeof(Stage) == 5120, "stage layout");
 
 // Statistics accumulator: fp32 partial sums over one tile of <= 16 values, folded into fp64 totals once per
 // tile (keeps the fp64 pipe and the F2F conversions out of the per-row instruction stream).
@@ -95,9 +85,9 @@ __device__ __forceinline__ void flush_stats(const Acc& a, const Acc& r, double* 
 // Stage hand-off: full (TMA) -> dready (delta warps) -> gready (chain) -> empty (epilogue), all mbarriers.
 // Requires B % 16 == 0 (16-byte global strides for the byte tensors) and 16-byte aligned bases.
 // ---------------------------------------------------------------------------------------------
-// ncu (round 1): with [16 x 32] boxes every role spent its time waiting for TMA although DRAM, L2 and the TMA pipe
-// were all < 10 % busy - the TMA unit retires roughly one box per 200-350 cycles per SM regardless of box size
-// (same rate seen with the 4 KB boxes of tc_wgrad_kernel), so bandwidth comes from BIG boxes: 64 steps per stage.
+// Box size (round 1): tools/tma_probe.cu pulls the three input arrays at 3.05 TB/s with [64 x 32] boxes but only
+// 1.76 TB/s with [16 x 32] boxes (per-box overhead), hence 64 steps per stage.  The loads are NOT what bounds this
+// kernel (a pure pull takes 8.3 us of the 16.7 us); the epilogue warps were - see the comment there.
 constexpr int kRW = 64;       // timesteps per TMA stage
 constexpr int kStagesWS = 4;  // 4 x 44.4 KB
 struct __align__(128) StageWS {
