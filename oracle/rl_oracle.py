@@ -173,6 +173,41 @@ def grpo_group_advantages(scores, loss_mask, group_size):
     return (torch.zeros_like(loss_mask) + a.reshape(1, -1)) * loss_mask
 
 
+def raw_advantages(rewards, loss_mask, normalize_advantages=False):
+    """rlinf/algorithms/advantages.py:410-438 (compute_raw_advantages): scores broadcast over the sequence,
+    optionally normalised over the valid entries (unbiased std, eps 1e-5).  [SURVEY §8(f) rank 4]"""
+    if rewards.ndim == 2:
+        rewards = rewards.reshape(-1)
+    adv = rewards.unsqueeze(0).expand_as(loss_mask) * loss_mask
+    if normalize_advantages:
+        valid = adv[loss_mask.bool()]
+        if valid.numel() > 0:
+            adv = (adv - valid.mean()) / (valid.std() + 1e-5)
+    return adv
+
+
+def reinpp_advantages(rewards, loss_mask, group_size, use_reinpp_baseline=False, kl_beta=0.0, logprob=None,
+                      ref_logprob=None, kl_penalty_type=""):
+    """rlinf/algorithms/advantages.py:302-364 (compute_reinpp_advantages): reward at the last valid token,
+    optional per-token KL penalty, reverse cumulative return over L, masked whitening with the BIASED variance
+    clamped at 1e-8 (rsqrt).  loss_mask is [L, B].  [SURVEY §8(f) rank 4]"""
+    if use_reinpp_baseline:
+        # the reference flattens the baselined rewards to 1-D and then scatters them with a 2-D index
+        # (advantages.py:331-345), which torch rejects: the option cannot be used in RLinf v0.4.0 either
+        raise IndexError("Dimension out of range (expected to be in range of [-1, 0], but got 1)")
+    L = loss_mask.size(0)
+    r = torch.zeros_like(loss_mask).float()
+    # NOTE the reference flips left-right (dim 1) and then argmax'es over dim 0 (advantages.py:339-341)
+    eos = L - 1 - loss_mask.long().fliplr().argmax(dim=0, keepdim=True)
+    r = r.scatter_(dim=0, index=eos, src=rewards.view(1, -1).float())
+    if kl_beta > 0:
+        r = r - kl_beta * kl_penalty(logprob, ref_logprob, kl_penalty_type)
+    ret = torch.cumsum(r.flip(dims=[0]), dim=0).flip(dims=[0])
+    mean = masked_mean(ret, loss_mask)
+    var = masked_mean((ret - mean).pow(2), loss_mask)
+    return (ret - mean) * var.clamp(min=1e-8).rsqrt()
+
+
 def adv_and_returns_embodied(adv_type, rewards, dones, values=None, loss_mask=None,
                              loss_mask_sum=None, gamma=1.0, gae_lambda=1.0, group_size=8,
                              reward_type="action_level", **kw):
@@ -317,7 +352,7 @@ def _to_rank(t, shape):
 
 def reduce_loss_inputs(logprobs, old_logprobs, advantages, logprob_type, single_action_dim,
                        loss_mask=None, loss_mask_sum=None, values=None, prev_values=None,
-                       returns=None, reward_type="action_level"):
+                       returns=None, reward_type="action_level", proximal_logprobs=None, versions=None):
     """rlinf/algorithms/utils.py:280-376 (preprocess_loss_inputs)."""
     if reward_type == "chunk_level":
         flat = lambda t: None if t is None else t.flatten()  # noqa: E731
@@ -330,14 +365,27 @@ def reduce_loss_inputs(logprobs, old_logprobs, advantages, logprob_type, single_
         advantages = advantages.unsqueeze(-1)
         loss_mask = None if loss_mask is None else loss_mask.unsqueeze(-1)
         loss_mask_sum = None if loss_mask_sum is None else loss_mask_sum.unsqueeze(-1)
+        if proximal_logprobs is not None:
+            proximal_logprobs = proximal_logprobs.reshape(bsz, -1, single_action_dim)
+        if versions is not None:
+            versions = versions.reshape(bsz, -1, single_action_dim)
     elif logprob_type == "action_level":
         logprobs = logprobs.reshape(bsz, -1, single_action_dim).sum(-1)
         old_logprobs = old_logprobs.reshape(bsz, -1, single_action_dim).sum(-1)
+        if proximal_logprobs is not None:
+            proximal_logprobs = proximal_logprobs.reshape(bsz, -1, single_action_dim).sum(-1)
+        if versions is not None:
+            versions = versions.reshape(bsz, -1, single_action_dim)[..., 0]
     elif logprob_type == "chunk_level":
         logprobs = logprobs.reshape(bsz, -1, single_action_dim).sum(dim=[1, 2])
         old_logprobs = old_logprobs.reshape(bsz, -1, single_action_dim).sum(dim=[1, 2])
+        if proximal_logprobs is not None:
+            proximal_logprobs = proximal_logprobs.reshape(bsz, -1, single_action_dim).sum(dim=[1, 2])
+        if versions is not None:
+            versions = versions.reshape(bsz, -1, single_action_dim)[:, 0, 0]
     shp = logprobs.shape
-    return dict(logprobs=logprobs, old_logprobs=old_logprobs,
+    return dict(logprobs=logprobs, old_logprobs=old_logprobs, proximal_logprobs=proximal_logprobs,
+                versions=_to_rank(versions, shp),
                 advantages=_to_rank(advantages, shp), loss_mask=_to_rank(loss_mask, shp),
                 loss_mask_sum=_to_rank(loss_mask_sum, shp), values=_to_rank(values, shp),
                 prev_values=_to_rank(prev_values, shp), returns=_to_rank(returns, shp))
@@ -399,6 +447,72 @@ def ppo_actor_loss(logprobs, old_logprobs, advantages, clip_ratio_low, clip_rati
     return loss, metrics
 
 
+def decoupled_ppo_actor_loss(logprobs, old_logprobs, advantages, clip_ratio_low, clip_ratio_high,
+                             proximal_logprobs=None, versions=None, current_version=None, loss_mask=None,
+                             clip_ratio_c=None, max_episode_steps=None, loss_mask_sum=None,
+                             critic_warmup=False, behave_weight_threshold=None, **_):
+    """rlinf/algorithms/losses.py:27-167 (compute_decoupled_ppo_actor_loss): PPO clipped around a proximal
+    policy (given, or interpolated between behaviour and current policy from the weight versions), importance
+    weight exp(prox - old) towards the behaviour policy with an optional cut-off.  [SURVEY §8(f) rank 4]"""
+    agg, wratio = masked_mean, None
+    if loss_mask is None:
+        loss_mask = torch.ones_like(logprobs).bool()
+    if max_episode_steps is not None and loss_mask_sum is not None and loss_mask is not None:
+        wratio = (loss_mask_sum * 1.0) / max_episode_steps
+        agg = masked_mean_ratio
+    if proximal_logprobs is None:
+        if versions is None or current_version is None:
+            proximal_logprobs = old_logprobs.detach()
+        else:
+            v_behav = versions.float()
+            v_theta = float(current_version)
+            v_prox = v_theta - 1.0
+            version_diff = v_theta - v_behav
+            version_gap = v_prox - v_behav
+            alpha = torch.where((version_diff > 0) & (versions >= 0), version_gap / version_diff,
+                                torch.zeros_like(v_behav))
+            while alpha.dim() < logprobs.dim():
+                alpha = alpha.unsqueeze(-1)
+            alpha = torch.clamp(alpha, 0.0, 1.0)
+            proximal_logprobs = (old_logprobs + alpha * (logprobs - old_logprobs)).detach()
+    cnt = loss_mask.count_nonzero() or 1  # int64 tensor (fp32 ratios below), as in the reference
+    prox_ratio = torch.where(loss_mask, torch.exp(logprobs - proximal_logprobs), 0.0)
+    clipped = torch.clamp(prox_ratio, 1.0 - clip_ratio_low, 1.0 + clip_ratio_high)
+    l1, l2 = -advantages * prox_ratio, -advantages * clipped
+    loss_e = torch.max(l1, l2)
+    if clip_ratio_c is not None:
+        assert clip_ratio_c > 1.0
+        l3 = torch.sign(advantages) * clip_ratio_c * advantages
+        dual_hit = l3.detach() < loss_e.detach()
+        loss_e = torch.min(loss_e, l3)
+    else:
+        dual_hit = torch.zeros_like(loss_e, dtype=torch.bool)
+    behav_weight = torch.exp(proximal_logprobs - old_logprobs)
+    behav_mask = ((behav_weight <= behave_weight_threshold).logical_and(loss_mask)
+                  if behave_weight_threshold is not None else loss_mask)
+    bcnt = behav_mask.count_nonzero() or 1
+    args = (behav_mask,) if agg is masked_mean else (behav_mask, wratio)
+    loss = agg(loss_e * behav_weight, *args)
+    if critic_warmup:
+        loss = torch.tensor(0.0)
+    with torch.no_grad():
+        metrics = {
+            "actor/policy_loss": loss.detach(),
+            "actor/proximal_ratio": masked_mean(prox_ratio.detach(), loss_mask),
+            "actor/clipped_proximal_ratio": masked_mean(clipped.detach(), loss_mask),
+            "actor/clip_fraction": (l1 < l2).logical_and(loss_mask).count_nonzero() / cnt,
+            "actor/dual_clip_fraction": dual_hit.logical_and(loss_mask).count_nonzero() / cnt,
+            "actor/behav_clip_fraction": 1.0 - (bcnt / cnt),
+            "actor/proximal_approx_kl": -torch.where(loss_mask, logprobs - proximal_logprobs, 0.0).sum() / cnt,
+            "actor/behav_approx_kl": -torch.where(behav_mask, proximal_logprobs - old_logprobs, 0.0).sum() / bcnt,
+        }
+        if (versions is not None and current_version is not None and versions.shape == loss_mask.shape
+                and bool(loss_mask.any())):
+            metrics["actor/average_version"] = versions[loss_mask].float().mean()
+            metrics["actor/current_version"] = torch.tensor(float(current_version))
+    return loss, metrics
+
+
 EV_PREFIX = "__sum__/_critic_explained_variance/"
 
 
@@ -436,13 +550,20 @@ def ppo_critic_loss(values, returns, prev_values, value_clip, huber_delta, loss_
 
 def policy_loss_embodied(loss_type, logprobs, old_logprobs, advantages, logprob_type,
                          single_action_dim, loss_mask=None, loss_mask_sum=None, values=None,
-                         prev_values=None, returns=None, reward_type="action_level", **hp):
-    """rlinf/algorithms/registry.py:77-92 (embodied) + losses.py:396-424,508-535."""
+                         prev_values=None, returns=None, reward_type="action_level", proximal_logprobs=None,
+                         versions=None, **hp):
+    """rlinf/algorithms/registry.py:77-92 (embodied) + losses.py:383-424,508-535."""
     p = reduce_loss_inputs(logprobs, old_logprobs, advantages, logprob_type, single_action_dim,
-                           loss_mask, loss_mask_sum, values, prev_values, returns, reward_type)
-    loss, metrics = ppo_actor_loss(p["logprobs"], p["old_logprobs"], p["advantages"],
-                                   loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"], **hp)
-    if loss_type == "actor_critic":
+                           loss_mask, loss_mask_sum, values, prev_values, returns, reward_type,
+                           proximal_logprobs, versions)
+    if loss_type == "decoupled_actor_critic":
+        loss, metrics = decoupled_ppo_actor_loss(p["logprobs"], p["old_logprobs"], p["advantages"],
+                                                 proximal_logprobs=p["proximal_logprobs"], versions=p["versions"],
+                                                 loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"], **hp)
+    else:
+        loss, metrics = ppo_actor_loss(p["logprobs"], p["old_logprobs"], p["advantages"],
+                                       loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"], **hp)
+    if loss_type in ("actor_critic", "decoupled_actor_critic"):
         closs, cmetrics = ppo_critic_loss(p["values"], p["returns"], p["prev_values"],
                                           hp["value_clip"], hp["huber_delta"],
                                           loss_mask=p["loss_mask"], loss_mask_sum=p["loss_mask_sum"],

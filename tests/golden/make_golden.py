@@ -259,11 +259,95 @@ def gen_policy(ref, out):
         out["pol_p3_" + n] = _np(p)
 
 
+def gen_next(ref, out):
+    """registry entries next in line (decoupled PPO loss, raw / reinforce++ advantages)."""
+    # ---- reasoning advantages: raw, reinpp ----
+    g = torch.Generator().manual_seed(11)
+    bsz, L, G = 24, 13, 4
+    rewards = torch.randn(bsz, generator=g)
+    lens = torch.randint(2, L + 1, (bsz,), generator=g)
+    mask = torch.arange(L)[None, :] < lens[:, None]
+    lp = -1 + 0.3 * torch.randn(bsz, L, generator=g)
+    rlp = lp + 0.1 * torch.randn(bsz, L, generator=g)
+    out["next_rewards"], out["next_mask"], out["next_lp"], out["next_rlp"] = _np(rewards), _np(mask), _np(lp), _np(rlp)
+    out["next_group_size"] = np.array([G], dtype=np.int64)
+    for name, kw in (("raw", dict(adv_type="raw", normalize_advantages=False)),
+                     ("raw_norm", dict(adv_type="raw", normalize_advantages=True)),
+                     ("reinpp", dict(adv_type="reinpp")),
+                     ("reinpp_kl", dict(adv_type="reinpp", kl_beta=0.05, logprob=lp, ref_logprob=rlp,
+                                        kl_penalty_type="k3"))):
+        a, r = ref.registry.calculate_adv_and_returns(task_type="reasoning", rewards=rewards.clone(), loss_mask=mask,
+                                                      group_size=G, **kw)
+        assert r is None
+        out["next_adv_" + name] = _np(a)
+    try:
+        ref.registry.calculate_adv_and_returns(task_type="reasoning", adv_type="reinpp", rewards=rewards.clone(),
+                                               loss_mask=mask, group_size=G, use_reinpp_baseline=True)
+        out["next_reinpp_baseline_raises"] = np.array([0])
+    except IndexError:
+        out["next_reinpp_baseline_raises"] = np.array([1])
+
+    # ---- decoupled PPO actor-critic loss ----
+    cases = []
+    specs = [
+        # name, seed, bsz, C, A, logprob_type, mask?, ratio-agg?, dual?, proximal (given/versions/none), threshold
+        ("dec_none", 0, 64, 1, 8, "action_level", False, False, False, "none", None),
+        ("dec_given_mask", 1, 72, 1, 8, "action_level", True, False, True, "given", 1.15),
+        ("dec_versions", 2, 48, 2, 7, "action_level", True, True, False, "versions", None),
+        ("dec_versions_chunk", 3, 40, 3, 7, "chunk_level", False, False, True, "versions", 1.05),
+    ]
+    for name, seed, bsz, C, A, lpt, use_mask, use_ratio, dual, prox, thr in specs:
+        g = torch.Generator().manual_seed(300 + seed)
+        old = -1.0 + 0.3 * torch.randn(bsz, C * A, generator=g)
+        new = (old + 0.15 * torch.randn(bsz, C * A, generator=g)).requires_grad_(True)
+        reward_type = "chunk_level" if lpt == "chunk_level" else "action_level"
+        per = 1 if reward_type == "chunk_level" else C
+        adv = torch.randn(bsz, per, generator=g)
+        ret = torch.randn(bsz, per, generator=g)
+        prev_v = torch.randn(bsz, per, generator=g)
+        val = (prev_v + 0.3 * torch.randn(bsz, per, generator=g)).requires_grad_(True)
+        mask = (torch.rand(bsz, per, generator=g) < 0.7) if use_mask else None
+        mask_sum = torch.randint(1, 50, (bsz, 1), generator=g).expand(bsz, per).contiguous() if use_mask else None
+        proximal = (old + 0.05 * torch.randn(bsz, C * A, generator=g)) if prox == "given" else None
+        versions = torch.randint(-1, 6, (bsz, 1), generator=g).expand(bsz, C * A).contiguous().float() \
+            if prox == "versions" else None
+        kw = dict(task_type="embodied", loss_type="decoupled_actor_critic", logprob_type=lpt, reward_type=reward_type,
+                  single_action_dim=A, logprobs=new, old_logprobs=old, advantages=adv, returns=ret, values=val,
+                  prev_values=prev_v, clip_ratio_high=0.28, clip_ratio_low=0.2, value_clip=0.2, huber_delta=1.5,
+                  loss_mask=mask, loss_mask_sum=mask_sum, max_episode_steps=50 if use_ratio else None,
+                  critic_warmup=False, proximal_logprobs=proximal, versions=versions,
+                  current_version=5.0 if prox == "versions" else None, behave_weight_threshold=thr)
+        if dual:
+            kw["clip_ratio_c"] = 3.0
+        loss, metrics = ref.registry.policy_loss(**kw)
+        loss.backward()
+        pre = f"dec_{name}_"
+        out[pre + "old"], out[pre + "new"], out[pre + "adv"] = _np(old), _np(new), _np(adv)
+        out[pre + "ret"], out[pre + "prev_v"], out[pre + "val"] = _np(ret), _np(prev_v), _np(val)
+        if mask is not None:
+            out[pre + "mask"], out[pre + "mask_sum"] = _np(mask), _np(mask_sum)
+        if proximal is not None:
+            out[pre + "proximal"] = _np(proximal)
+        if versions is not None:
+            out[pre + "versions"] = _np(versions)
+        out[pre + "cfg"] = np.array([bsz, C, A, int(use_ratio), int(dual), -1 if thr is None else 1], dtype=np.int64)
+        out[pre + "thr"] = np.array([0.0 if thr is None else thr], dtype=np.float64)
+        out[pre + "types"] = np.array([lpt, reward_type, prox])
+        out[pre + "loss"] = _np(loss)
+        out[pre + "dnew"] = _np(new.grad if new.grad is not None else torch.zeros_like(new))
+        out[pre + "dval"] = _np(val.grad if val.grad is not None else torch.zeros_like(val))
+        keys = sorted(metrics)
+        out[pre + "metric_keys"] = np.array(keys)
+        out[pre + "metric_vals"] = np.array([float(metrics[k]) for k in keys], dtype=np.float64)
+        cases.append(name)
+    out["dec_cases"] = np.array(cases)
+
+
 def main():
     ref = load_reference()
     torch.set_num_threads(1)
     for fn, name in ((gen_adv, "adv"), (gen_loss, "loss"), (gen_indexing, "indexing"), (gen_policy, "policy"),
-                     (gen_filter_and_metrics, "filter")):
+                     (gen_filter_and_metrics, "filter"), (gen_next, "next")):
         out = {}
         fn(ref, out)
         path = os.path.join(HERE, f"golden_{name}.npz")
