@@ -20,6 +20,7 @@
 #include <curand_kernel.h>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"  // rb::tc::g_debug_flags (experiment switches)
 
 namespace {
 
@@ -137,25 +138,118 @@ __device__ __forceinline__ void layer_tiled(const float* __restrict__ in_s, int 
                     tanh_fast(acc[e].w + b.w));
 }
 
-// EMAX == 32 (up to 32 environments per CTA) uses the register-tiled layer, smaller slices the column-per-thread one
-template <int EMAX>
+// ---- experimental deeper software pipelining (rb200_debug_set_flags bit 1; NOT validated on a GPU yet) ----------
+// Same arithmetic, same k-ascending fmaf order (bit-identical results), but the weight rows of the next D k-steps
+// are in flight instead of one: with 8 warps / SM the one-k-step prefetch leaves the L2 latency exposed (round 1:
+// 45 us / env step at E = 4 although the FMA work is ~2 us).  Requires K % (4 * D) == 0.
+template <int EMAX, int D>
+__device__ __forceinline__ void layer_pf(const float* __restrict__ in_s, int K, const float* __restrict__ Wt,
+                                         const float* __restrict__ bias, float* __restrict__ out_s, int j) {
+  float acc[EMAX];
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) acc[e] = 0.f;
+  float w[D][4];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[d][i] = __ldg(Wt + (size_t)(4 * d + i) * kH + j);
+  for (int k = 0; k < K; k += 4 * D) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int kk = k + 4 * d;
+      const float w0 = w[d][0], w1 = w[d][1], w2 = w[d][2], w3 = w[d][3];
+      if (kk + 4 * D < K) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[d][i] = __ldg(Wt + (size_t)(kk + 4 * D + i) * kH + j);
+      }
+#pragma unroll
+      for (int e = 0; e < EMAX; ++e) {
+        const float4 xv = *reinterpret_cast<const float4*>(in_s + e * K + kk);
+        acc[e] = fmaf(xv.x, w0, acc[e]);
+        acc[e] = fmaf(xv.y, w1, acc[e]);
+        acc[e] = fmaf(xv.z, w2, acc[e]);
+        acc[e] = fmaf(xv.w, w3, acc[e]);
+      }
+    }
+  }
+  const float b = bias[j];
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) out_s[e * kH + j] = tanh_fast(acc[e] + b);
+}
+
+template <int EMAX, int D>
+__device__ __forceinline__ void layer_tiled_pf(const float* __restrict__ in_s, int K, const float* __restrict__ Wt,
+                                               const float* __restrict__ bias, float* __restrict__ out_s, int tid) {
+  constexpr int ET = EMAX / 4;
+  const int cg = tid & 63, eg = tid >> 6;
+  const float* in_e = in_s + (size_t)eg * ET * K;
+  const float4* W4 = reinterpret_cast<const float4*>(Wt) + cg;
+  float4 acc[ET];
+#pragma unroll
+  for (int e = 0; e < ET; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[D][4];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[d][i] = __ldg(W4 + (size_t)(4 * d + i) * 64);
+  for (int k = 0; k < K; k += 4 * D) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int kk = k + 4 * d;
+      const float4 w0 = w[d][0], w1 = w[d][1], w2 = w[d][2], w3 = w[d][3];
+      if (kk + 4 * D < K) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[d][i] = __ldg(W4 + (size_t)(kk + 4 * D + i) * 64);
+      }
+#pragma unroll
+      for (int e = 0; e < ET; ++e) {
+        const float4 xv = *reinterpret_cast<const float4*>(in_e + e * K + kk);
+        acc[e].x = fmaf(xv.x, w0.x, acc[e].x); acc[e].y = fmaf(xv.x, w0.y, acc[e].y);
+        acc[e].z = fmaf(xv.x, w0.z, acc[e].z); acc[e].w = fmaf(xv.x, w0.w, acc[e].w);
+        acc[e].x = fmaf(xv.y, w1.x, acc[e].x); acc[e].y = fmaf(xv.y, w1.y, acc[e].y);
+        acc[e].z = fmaf(xv.y, w1.z, acc[e].z); acc[e].w = fmaf(xv.y, w1.w, acc[e].w);
+        acc[e].x = fmaf(xv.z, w2.x, acc[e].x); acc[e].y = fmaf(xv.z, w2.y, acc[e].y);
+        acc[e].z = fmaf(xv.z, w2.z, acc[e].z); acc[e].w = fmaf(xv.z, w2.w, acc[e].w);
+        acc[e].x = fmaf(xv.w, w3.x, acc[e].x); acc[e].y = fmaf(xv.w, w3.y, acc[e].y);
+        acc[e].z = fmaf(xv.w, w3.z, acc[e].z); acc[e].w = fmaf(xv.w, w3.w, acc[e].w);
+      }
+    }
+  }
+  const float4 b = *reinterpret_cast<const float4*>(bias + 4 * cg);
+#pragma unroll
+  for (int e = 0; e < ET; ++e)
+    *reinterpret_cast<float4*>(out_s + (size_t)(eg * ET + e) * kH + 4 * cg) =
+        make_float4(tanh_fast(acc[e].x + b.x), tanh_fast(acc[e].y + b.y), tanh_fast(acc[e].z + b.z),
+                    tanh_fast(acc[e].w + b.w));
+}
+
+// EMAX == 32 (up to 32 environments per CTA) uses the register-tiled layer, smaller slices the column-per-thread one.
+// PF = weight prefetch depth of the experimental variants (0 = the validated kernels).
+template <int EMAX, int PF>
 __device__ __forceinline__ void layer_any(const float* __restrict__ in_s, int K, const float* __restrict__ Wt,
                                           const float* __restrict__ bias, float* __restrict__ out_s, int j) {
+  if constexpr (PF > 0) {
+    if (K % (4 * PF) == 0) {  // uniform
+      if constexpr (EMAX >= 32) layer_tiled_pf<EMAX, (PF > 2 ? 2 : PF)>(in_s, K, Wt, bias, out_s, j);
+      else layer_pf<EMAX, PF>(in_s, K, Wt, bias, out_s, j);
+      return;
+    }
+  }
   if constexpr (EMAX >= 32) layer_tiled<EMAX>(in_s, K, Wt, bias, out_s, j);
   else layer<EMAX>(in_s, K, Wt, bias, out_s, j);
 }
 
 // value tower on in_s -> g3 in bufB (uses bufC as the middle buffer); every thread must call it
-template <int EMAX>
+template <int EMAX, int PF>
 __device__ __forceinline__ void value_tower(const FusedArgs& p, const float* in_s, float* bufB, float* bufC, int j) {
   const float* P = p.params;
   const float* wt_v = p.wt;  // value tower first
   const size_t n0 = (size_t)p.obs * kH, nn = (size_t)kH * kH;
-  layer_any<EMAX>(in_s, p.obs, wt_v, P + p.L.vb0, bufB, j);
+  layer_any<EMAX, PF>(in_s, p.obs, wt_v, P + p.L.vb0, bufB, j);
   __syncthreads();
-  layer_any<EMAX>(bufB, kH, wt_v + n0, P + p.L.vb1, bufC, j);
+  layer_any<EMAX, PF>(bufB, kH, wt_v + n0, P + p.L.vb1, bufC, j);
   __syncthreads();
-  layer_any<EMAX>(bufC, kH, wt_v + n0 + nn, P + p.L.vb2, bufB, j);
+  layer_any<EMAX, PF>(bufC, kH, wt_v + n0 + nn, P + p.L.vb2, bufB, j);
   __syncthreads();
 }
 
@@ -170,7 +264,7 @@ __device__ __forceinline__ float value_dot(const float* g3_row, const float* s_v
   return rb::warp_sum(s);
 }
 
-template <int EMAX>
+template <int EMAX, int PF>
 __global__ void __launch_bounds__(kThreads, 1) rollout_fused_kernel(FusedArgs p) {
   extern __shared__ __align__(16) float sm[];
   const int obs = p.obs, act = p.act;
@@ -213,14 +307,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fused_kernel(FusedArgs p)
 
   for (int t = 0; t < T; ++t) {
     // ---- actor tower: x -> bufA -> bufB -> bufA (h3) ----
-    layer_any<EMAX>(x, obs, wt_b, P + p.L.bb0, bufA, j);
+    layer_any<EMAX, PF>(x, obs, wt_b, P + p.L.bb0, bufA, j);
     __syncthreads();
-    layer_any<EMAX>(bufA, kH, wt_b + n0, P + p.L.bb1, bufB, j);
+    layer_any<EMAX, PF>(bufA, kH, wt_b + n0, P + p.L.bb1, bufB, j);
     __syncthreads();
-    layer_any<EMAX>(bufB, kH, wt_b + n0 + nn, P + p.L.bb2, bufA, j);
+    layer_any<EMAX, PF>(bufB, kH, wt_b + n0 + nn, P + p.L.bb2, bufA, j);
     __syncthreads();
     // ---- value tower: x -> bufB -> bufC -> bufB (g3) ----
-    if (has_v) value_tower<EMAX>(p, x, bufB, bufC, j);
+    if (has_v) value_tower<EMAX, PF>(p, x, bufB, bufC, j);
 
     // ---- heads: one warp per environment (head_fwd_kernel, sample mode) ----
     for (int e = warp; e < nE; e += kThreads / 32) {
@@ -339,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fused_kernel(FusedArgs p)
       if (j < nE) any = flag_s[j];
       any = __syncthreads_or(any);
       if (any) {
-        value_tower<EMAX>(p, zs, bufB, bufC, j);
+        value_tower<EMAX, PF>(p, zs, bufB, bufC, j);
         for (int e = warp; e < nE; e += kThreads / 32) {
           if (!flag_s[e]) continue;
           const float v = value_dot(bufB + e * kH, s_vw, lane);
@@ -357,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fused_kernel(FusedArgs p)
 
   // ---- bootstrap value row T (env_worker.py:1237-1306) ----
   if (has_v) {
-    value_tower<EMAX>(p, x, bufB, bufC, j);
+    value_tower<EMAX, PF>(p, x, bufB, bufC, j);
     for (int e = warp; e < nE; e += kThreads / 32) {
       const float v = value_dot(bufB + e * kH, s_vw, lane);
       if (lane == 0) p.values[(size_t)T * B + e0 + e] = v;
@@ -390,17 +484,23 @@ size_t fused_smem(int obs) {
          sizeof(int) * 2 * EMAX;
 }
 
-template <int EMAX>
-int launch_fused(const FusedArgs& a, int grid, cudaStream_t st) {
+template <int EMAX, int PF>
+int launch_fused_pf(const FusedArgs& a, int grid, cudaStream_t st) {
   const size_t smem = fused_smem<EMAX>(a.obs);
   if (smem > 227 * 1024) return RB200_E_UNSUPPORTED;
-  cudaError_t ce = cudaFuncSetAttribute(rollout_fused_kernel<EMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t ce = cudaFuncSetAttribute(rollout_fused_kernel<EMAX, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem);
   if (ce != cudaSuccess) return (int)ce;
-  rollout_fused_kernel<EMAX><<<grid, kThreads, smem, st>>>(a);
+  rollout_fused_kernel<EMAX, PF><<<grid, kThreads, smem, st>>>(a);
   rb::count_launch();
   ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+template <int EMAX>
+int launch_fused(const FusedArgs& a, int grid, cudaStream_t st) {
+  if (rb::tc::g_debug_flags & 2) return launch_fused_pf<EMAX, 4>(a, grid, st);  // experimental deeper prefetch
+  return launch_fused_pf<EMAX, 0>(a, grid, st);
 }
 
 }  // namespace

@@ -21,8 +21,8 @@ struct Params {
 };
 
 // debug/experiment switches (rb200_debug_set_flags): bit 0 = also mask the streamed operand's hi part in shared memory
-// (default off: the tensor core ignores the low 13 mantissa bits of a kind::tf32 operand - verified bit-identical), bits 8.. = L2 prefetch
-// distance in k-blocks (0 = default)
+// (default off: the tensor core ignores the low 13 mantissa bits of a kind::tf32 operand - verified bit-identical), bit 1 = fused rollout kernel
+// with deeper weight prefetch (experimental), bits 8.. = L2 prefetch distance in k-blocks (0 = default)
 extern int g_debug_flags;
 
 // C[M,256] = epi( A[M,K] . (B_hi+B_lo)[256,K]^T ).  A is plain fp32 (split into exact-TF32 hi/lo inside the kernel);

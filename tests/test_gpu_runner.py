@@ -1,5 +1,7 @@
 """GPU end-to-end parity: device rollout buffer alignment, synthetic env, and the PPO update
 (shuffle -> micro-batches -> fused loss -> backward -> clip+AdamW) against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -144,6 +146,38 @@ def test_fused_rollout_matches_per_kernel_path(B):
         torch.testing.assert_close(a["forward_inputs"]["states"], b["forward_inputs"]["states"], rtol=2e-3, atol=2e-4)
         torch.testing.assert_close(a["forward_inputs"]["action"], b["forward_inputs"]["action"], rtol=2e-3, atol=2e-4)
     assert bool(bufs[0][2]["dones"].any())
+
+
+@pytest.mark.skipif(os.environ.get("RB200_EXPERIMENTAL", "0") != "1",
+                    reason="experimental kernel variants (rb200_debug_set_flags): RB200_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("B", [300, 1000, 2000, 4096])
+def test_experimental_fused_rollout_prefetch_variants_bit_identical(B):
+    """Deeper weight prefetch (debug flag bit 1) keeps the k-ascending fmaf order: buffers must be bit-identical
+    to the validated fused kernels."""
+    from rlinf_b200 import _lib as L
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    T, obs, act = 6, 16, 3
+    outs = []
+    try:
+        for flags in (0, 2):
+            L.load().rb200_debug_set_flags(flags)
+            cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, **{"rollout.fused_kernel": True,
+                                                                                  "env.train.p_term": 0.03,
+                                                                                  "env.train.max_episode_steps": 5})
+            run = EmbodiedRunner(cfg)
+            for _ in range(2):
+                run.rollout_phase()
+            torch.cuda.synchronize()
+            outs.append(_cpu_batch(run.buffer.as_batch()))
+    finally:
+        L.load().rb200_debug_set_flags(0)
+    a, b = outs
+    for k in ("dones", "terminations", "truncations", "rewards", "prev_values", "prev_logprobs"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a["forward_inputs"]["states"], b["forward_inputs"]["states"])
+    assert torch.equal(a["forward_inputs"]["action"], b["forward_inputs"]["action"])
 
 
 @pytest.mark.parametrize("accum", [1, 2])
