@@ -48,6 +48,8 @@ def parse():
                     help="envs in the bounded CPU sample (0 = 512 for cpu_baseline, 256 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-bench", action="store_true")
+    ap.add_argument("--debug-flags", type=int, default=0,
+                    help="rb200_debug_set_flags value (experimental kernel variants; 0 = shipped kernels)")
     ap.add_argument("--rollout", default="auto", choices=["auto", "fused", "graph"],
                     help="rollout implementation: persistent fused kernel, per-kernel CUDA graph, or the library default")
     return ap.parse_args()
@@ -310,6 +312,8 @@ def run_ours(a):
     from rlinf_b200.runner import EmbodiedRunner
 
     lib = L.load()
+    if a.debug_flags:
+        lib.rb200_debug_set_flags(int(a.debug_flags))
     peaks = measured_peaks()
     over = {} if a.rollout == "auto" else {"rollout.fused_kernel": a.rollout == "fused"}
     cfg = synthetic_ppo_config(B=a.B, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
