@@ -271,7 +271,7 @@ int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN,
 
 /* Experiment switches of the tensor-core kernels (tools/ only; default 0): bit 0 = additionally mask the streamed operand's
  * hi part in shared memory (not needed: the tensor core truncates), bit 1 = fused-rollout variants with a 4-k-step weight
- * prefetch (experimental), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
+ * prefetch (experimental), bit 2 = cta_group::2 (CTA-pair) forward/dgrad GEMM (experimental), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
 int rb200_debug_set_flags(int flags);
 
 /* Persistent fused rollout (csrc/rollout_fused.cu): the whole T-step loop of one rank - MLP actor/critic inference,
