@@ -173,6 +173,51 @@ def grpo_group_advantages(scores, loss_mask, group_size):
     return (torch.zeros_like(loss_mask) + a.reshape(1, -1)) * loss_mask
 
 
+def grpo_video_advantages(rewards, loss_mask, group_size, advantage_mode):
+    """rlinf/algorithms/advantages.py:124-164 (compute_grpo_video_advantages): per-frame ("frame") or per-video
+    ("video") group normalisation of step-level rewards [num_steps, B], unbiased std, eps 1e-6 on the std."""
+    num_steps, batch = rewards.shape
+    g = rewards.reshape(num_steps, -1, group_size)
+    if advantage_mode == "frame":
+        mean, std = g.mean(dim=-1, keepdim=True), g.std(dim=-1, keepdim=True)
+    elif advantage_mode == "video":
+        mean, std = g.mean(dim=(0, 2), keepdim=True), g.std(dim=(0, 2), keepdim=True)
+    else:
+        raise ValueError(f"Unsupported grpo_video advantage_mode: {advantage_mode}")
+    return ((g - mean) / (std + 1e-6)).reshape(num_steps, batch) * loss_mask
+
+
+def opd_advantages(prev_logprobs, teacher_logprobs, num_action_chunks, loss_mask=None):
+    """rlinf/algorithms/advantages.py:367-407 (compute_opd_advantages): dense reverse-KL reward
+    teacher_logp - student_logp per token, reshaped to [..., num_action_chunks, tokens_per_chunk]; a bootstrap row
+    beyond the loss mask's time dimension is dropped."""
+    adv = teacher_logprobs.float() - prev_logprobs.float()
+    assert adv.shape[-1] % num_action_chunks == 0
+    adv = adv.reshape(*adv.shape[:-1], num_action_chunks, -1)
+    if loss_mask is not None:
+        adv = adv[: loss_mask.shape[0]]
+    return adv
+
+
+def opd_actor_loss(logprobs, advantages, loss_mask, loss_mask_sum, max_episode_steps=None):
+    """rlinf/algorithms/losses.py:427-505 (compute_opd_actor_loss): -logp * stop_grad(reward), masked mean (or the
+    per-episode ratio aggregation); the mask / mask_sum broadcast over the token dimension."""
+    if loss_mask.dim() == logprobs.dim() - 1:
+        loss_mask = loss_mask.unsqueeze(-1)
+    if loss_mask_sum.dim() == logprobs.dim() - 1:
+        loss_mask_sum = loss_mask_sum.unsqueeze(-1)
+    loss_mask = loss_mask.expand_as(logprobs)
+    loss_mask_sum = loss_mask_sum.expand_as(logprobs)
+    r = advantages.detach()
+    if max_episode_steps is not None:
+        loss = masked_mean_ratio(-logprobs * r, loss_mask, (loss_mask_sum * 1.0) / max_episode_steps)
+    else:
+        loss = masked_mean(-logprobs * r, loss_mask)
+    metrics = {"actor/policy_loss": loss.detach(), "actor/opd_reward": masked_mean(r, loss_mask).detach(),
+               "actor/opd_reverse_kl": masked_mean(-r, loss_mask).detach()}
+    return loss, metrics
+
+
 def raw_advantages(rewards, loss_mask, normalize_advantages=False):
     """rlinf/algorithms/advantages.py:410-438 (compute_raw_advantages): scores broadcast over the sequence,
     optionally normalised over the valid entries (unbiased std, eps 1e-5).  [SURVEY §8(f) rank 4]"""

@@ -342,6 +342,45 @@ def gen_next(ref, out):
         cases.append(name)
     out["dec_cases"] = np.array(cases)
 
+    # ---- grpo_video advantages (step-level video rewards) ----
+    g = torch.Generator().manual_seed(21)
+    steps, B, G = 7, 24, 4
+    vr = torch.randn(steps, B, generator=g)
+    vm = (torch.rand(steps, B, generator=g) < 0.8).float()
+    out["vid_rewards"], out["vid_mask"] = _np(vr), _np(vm)
+    for mode in ("frame", "video"):
+        a, r = ref.advantages.compute_grpo_video_advantages(rewards=vr.clone(), loss_mask=vm, group_size=G,
+                                                            advantage_mode=mode)
+        assert r is None
+        out["vid_adv_" + mode] = _np(a)
+
+    # ---- OPD (on-policy distillation): advantages + actor loss ----
+    g = torch.Generator().manual_seed(22)
+    Tn, B, C, tok = 6, 10, 2, 7
+    student = -1.0 + 0.3 * torch.randn(Tn + 1, B, C * tok, generator=g)
+    teacher = student + 0.2 * torch.randn(Tn + 1, B, C * tok, generator=g)
+    lmask = torch.rand(Tn, B, C, generator=g) < 0.8
+    a, r = ref.advantages.compute_opd_advantages(prev_logprobs=student, teacher_logprobs=teacher, loss_mask=lmask,
+                                                 normalize_advantages=False, num_action_chunks=C)
+    assert r is None
+    out["opd_student"], out["opd_teacher"], out["opd_mask"], out["opd_adv"] = _np(student), _np(teacher), _np(lmask), _np(a)
+    n = Tn * B
+    lp = (student[:Tn].reshape(n, C, tok) + 0.05 * torch.randn(n, C, tok, generator=g)).requires_grad_(True)
+    adv = a.reshape(n, C, tok).contiguous()
+    m2 = lmask.reshape(n, C)
+    msum = torch.randint(1, 40, (n, 1), generator=g).expand(n, C).contiguous()
+    for name, mes in (("mean", None), ("ratio", 50)):
+        if lp.grad is not None:
+            lp.grad = None
+        loss, metrics = ref.losses.compute_opd_actor_loss(logprobs=lp, advantages=adv, loss_mask=m2, loss_mask_sum=msum,
+                                                          max_episode_steps=mes)
+        loss.backward()
+        out[f"opd_{name}_loss"], out[f"opd_{name}_dlp"] = _np(loss), _np(lp.grad)
+        keys = sorted(metrics)
+        out[f"opd_{name}_metric_keys"] = np.array(keys)
+        out[f"opd_{name}_metric_vals"] = np.array([float(metrics[k]) for k in keys], dtype=np.float64)
+    out["opd_lp"], out["opd_msum"] = _np(lp), _np(msum)
+
 
 def main():
     ref = load_reference()
