@@ -506,20 +506,17 @@ def decoupled_ppo_actor_loss(logprobs, old_logprobs, advantages, clip_ratio_low,
         wratio = (loss_mask_sum * 1.0) / max_episode_steps
         agg = masked_mean_ratio
     if proximal_logprobs is None:
-        if versions is None or current_version is None:
-            proximal_logprobs = old_logprobs.detach()
-        else:
-            v_behav = versions.float()
-            v_theta = float(current_version)
-            v_prox = v_theta - 1.0
-            version_diff = v_theta - v_behav
-            version_gap = v_prox - v_behav
-            alpha = torch.where((version_diff > 0) & (versions >= 0), version_gap / version_diff,
-                                torch.zeros_like(v_behav))
-            while alpha.dim() < logprobs.dim():
-                alpha = alpha.unsqueeze(-1)
-            alpha = torch.clamp(alpha, 0.0, 1.0)
-            proximal_logprobs = (old_logprobs + alpha * (logprobs - old_logprobs)).detach()
+        anchor = old_logprobs.detach()
+        if versions is not None and current_version is not None:
+            # anchor = behaviour policy moved a fraction w towards the current one, w = (age - 1) / age with
+            # age = current weight version - version that generated the sample (0 where age <= 0 or version < 0)
+            cur = float(current_version)
+            born = versions.float()
+            age = cur - born
+            w = torch.where((age > 0) & (versions >= 0), ((cur - 1.0) - born) / age, torch.zeros_like(born))
+            w = w.reshape(w.shape + (1,) * (logprobs.dim() - w.dim())).clamp(0.0, 1.0)
+            anchor = (old_logprobs + w * (logprobs - old_logprobs)).detach()
+        proximal_logprobs = anchor
     cnt = loss_mask.count_nonzero() or 1  # int64 tensor (fp32 ratios below), as in the reference
     prox_ratio = torch.where(loss_mask, torch.exp(logprobs - proximal_logprobs), 0.0)
     clipped = torch.clamp(prox_ratio, 1.0 - clip_ratio_low, 1.0 + clip_ratio_high)
