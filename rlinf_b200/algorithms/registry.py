@@ -24,32 +24,37 @@ ADV_REGISTRY: dict[str, Callable] = {}
 LOSS_REGISTRY: dict[str, Callable] = {}
 
 
-def register_advantage(name: str):
-    def decorator(fn):
-        ADV_REGISTRY[name.lower()] = fn
-        return fn
+def _registrar(table: dict):
+    """Decorator factory shared by both tables; keys are stored lower-cased, as the reference does."""
 
-    return decorator
+    def register(name: str):
+        def bind(fn):
+            table[name.lower()] = fn
+            return fn
+
+        return bind
+
+    return register
+
+
+register_advantage = _registrar(ADV_REGISTRY)      # registry.py:33
+register_policy_loss = _registrar(LOSS_REGISTRY)   # registry.py:59
 
 
 def get_adv_and_returns(name: str) -> Callable:
-    if name.lower() not in ADV_REGISTRY:
+    """Case-insensitive lookup (registry.py:47); unknown names raise the reference's message."""
+    fn = ADV_REGISTRY.get(name.lower())
+    if fn is None:
         raise ValueError(f"Advantage '{name}' not registered. Available: {list(ADV_REGISTRY.keys())}")
-    return ADV_REGISTRY[name.lower()]
-
-
-def register_policy_loss(name: str):
-    def decorator(fn):
-        LOSS_REGISTRY[name.lower()] = fn
-        return fn
-
-    return decorator
+    return fn
 
 
 def get_policy_loss(name: str):
-    if name not in LOSS_REGISTRY:
-        raise ValueError(f"Loss {name} not registered")
-    return LOSS_REGISTRY[name]
+    """Exact-key lookup (registry.py:71: no lower-casing on this side)."""
+    try:
+        return LOSS_REGISTRY[name]
+    except KeyError:
+        raise ValueError(f"Loss {name} not registered") from None
 
 
 def policy_loss(**kwargs) -> tuple[torch.Tensor, dict]:
