@@ -84,3 +84,23 @@ def test_shard_errors():
         D.shard_envs(64, 2, 0, group_size=5)
     with pytest.raises(AssertionError):
         D.per_rank_batch(1000, 2, 300, 4000)
+
+
+def test_bench_sharding_arithmetic_for_1_2_4_8_ranks():
+    """The headline config (B=4096, T=512, 8 mini-batches) splits evenly for every N the scaling run uses: per-rank
+    envs, per-rank share of the global batch, micro-batch count (the N=2 run once failed on exactly this)."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.dist_utils import per_rank_batch, shard_envs
+
+    B, T = 4096, 512
+    for world in (1, 2, 4, 8):
+        cfg = synthetic_ppo_config(B=B, T=T, world_size=world)
+        covered = []
+        for rank in range(world):
+            start, n = shard_envs(cfg.env.train.total_num_envs, world, rank, cfg.algorithm.get("group_size", 1))
+            covered.append((start, n))
+            per_rank, accum, n_global = per_rank_batch(cfg.actor.global_batch_size, world, cfg.actor.micro_batch_size,
+                                                       n * T)
+            assert per_rank == cfg.actor.global_batch_size // world and accum == 1
+            assert (n * T) % per_rank == 0 and (n * T) // per_rank == 8  # 8 optimiser steps per epoch on every rank
+        assert covered == [(r * B // world, B // world) for r in range(world)]
