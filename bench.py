@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-kernel-bench", action="store_true")
     ap.add_argument("--debug-flags", type=int, default=0,
                     help="rb200_debug_set_flags value (experimental kernel variants; 0 = shipped kernels)")
+    ap.add_argument("--graph-update", action="store_true",
+                    help="experimental: replay one CUDA graph per optimiser step (actor.cuda_graph_update)")
     ap.add_argument("--rollout", default="auto", choices=["auto", "fused", "graph"],
                     help="rollout implementation: persistent fused kernel, per-kernel CUDA graph, or the library default")
     return ap.parse_args()
@@ -316,6 +318,8 @@ def run_ours(a):
         lib.rb200_debug_set_flags(int(a.debug_flags))
     peaks = measured_peaks()
     over = {} if a.rollout == "auto" else {"rollout.fused_kernel": a.rollout == "fused"}
+    if a.graph_update:
+        over["actor.cuda_graph_update"] = True
     cfg = synthetic_ppo_config(B=a.B, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
                                num_minibatches=a.minibatches, world_size=world, **over)
     run = EmbodiedRunner(cfg)

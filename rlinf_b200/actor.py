@@ -84,6 +84,12 @@ class EmbodiedActor:
         self.rollout_batch: dict = {}
         self._perm_cache: dict = {}
         self.version = 0
+        # EXPERIMENTAL (actor.cuda_graph_update, default off, not yet validated on a GPU): replay one CUDA graph per
+        # mini-batch instead of ~35 ctypes launches - the update of small per-rank batches is launch-bound
+        self._graph_update = bool(self.cfg.actor.get("cuda_graph_update", False))
+        self._static_batch: dict = {}
+        self._step_graphs: dict = {}
+        self._train_calls = 0
 
     # ---- rollout intake ---------------------------------------------------------------------------
     def recv_rollout_trajectories(self, batch: dict) -> None:
@@ -161,8 +167,20 @@ class EmbodiedActor:
         step_rows = torch.zeros(n_steps, 4, dtype=torch.float64, device=self.device)
         lr_rows = []
         mi = si = 0
+        graphed = self._graph_update and self._train_calls > 0  # the first call runs eagerly (lazy initialisation)
+        self._train_calls += 1
+        if graphed:
+            batch = self._persist_batch(batch)
+            self.rollout_batch = batch
         for _ in range(update_epoch):
             for gb in range(n_global):
+                if graphed:
+                    self._graphed_step(batch, gb, batch_size_per_rank, mbs, metric_rows[mi: mi + self.gradient_accumulation],
+                                       step_rows[si])
+                    mi += self.gradient_accumulation
+                    lr_rows.append(self.optimizer.lr_list())
+                    si += 1
+                    continue
                 self.optimizer.zero_grad()
                 for k in range(self.gradient_accumulation):
                     lo = gb * batch_size_per_rank + k * mbs
@@ -174,6 +192,58 @@ class EmbodiedActor:
                 si += 1
         self.optimizer.zero_grad()
         return self._reduce_metrics(metric_rows, step_rows, lr_rows)
+
+    # ---- experimental: CUDA-graphed optimiser step -------------------------------------------------
+    def _persist_batch(self, batch: dict, prefix: str = "") -> dict:
+        """Copy the shuffled training batch into buffers with stable addresses (graphs bake pointers)."""
+        out = {}
+        for k, v in batch.items():
+            key = prefix + k
+            if isinstance(v, dict):
+                out[k] = self._persist_batch(v, key + "/")
+            elif isinstance(v, torch.Tensor):
+                buf = self._static_batch.get(key)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = torch.empty_like(v)
+                    self._static_batch[key] = buf
+                    self._step_graphs.clear()  # addresses changed
+                buf.copy_(v)
+                out[k] = buf
+            else:
+                out[k] = v
+        return out
+
+    def _graphed_step(self, batch, gb, batch_size_per_rank, mbs, metric_out, state_out) -> None:
+        """zero_grad + micro-batches (graph A) | gradient all-reduce (eager, world > 1) | clip + AdamW (graph B)."""
+        warm = self.optimizer_steps < self.critic_warmup_steps
+        accum = self.gradient_accumulation
+        key = (gb, warm, accum, mbs, batch_size_per_rank, tuple(self.optimizer.lr_list()), self._world_size)
+        entry = self._step_graphs.get(key)
+        if entry is None:
+            stage_m = torch.zeros(accum, L.NUM_METRICS, dtype=torch.float32, device=self.device)
+            stage_s = torch.zeros(4, dtype=torch.float64, device=self.device)
+            torch.cuda.synchronize()
+            self.model.mark_params_changed()  # the weight-split refresh must be part of graph A
+            g_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_a):
+                self.optimizer.zero_grad()
+                for k in range(accum):
+                    lo = gb * batch_size_per_rank + k * mbs
+                    self.train_micro_batch(batch, lo, lo + mbs, stage_m[k])
+            g_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_b, pool=g_a.pool()):
+                self.optimizer.step(grad_scale=1.0 / self._world_size)
+                stage_s.copy_(self.optimizer.state)
+            entry = (g_a, g_b, stage_m, stage_s)
+            self._step_graphs[key] = entry
+        g_a, g_b, stage_m, stage_s = entry
+        g_a.replay()
+        self.optimizer_steps += 1
+        D.allreduce_flat_grads(self.model.flat_grads, self._world_size, self.pg)
+        g_b.replay()
+        self.model.mark_params_changed()
+        metric_out.copy_(stage_m)
+        state_out.copy_(stage_s)
 
     def train_micro_batch(self, batch, lo, hi, metric_out) -> None:
         cfg = self.cfg

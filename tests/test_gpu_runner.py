@@ -180,6 +180,31 @@ def test_experimental_fused_rollout_prefetch_variants_bit_identical(B):
     assert torch.equal(a["forward_inputs"]["action"], b["forward_inputs"]["action"])
 
 
+@pytest.mark.skipif(os.environ.get("RB200_EXPERIMENTAL", "0") != "1",
+                    reason="experimental CUDA-graphed optimiser step: RB200_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("accum", [1, 2])
+def test_experimental_graphed_update_matches_eager(accum):
+    """actor.cuda_graph_update replays the same kernels: parameters after 3 iterations agree with the eager loop
+    (atomics in the weight-gradient kernels make it allclose, not bit-equal)."""
+    from rlinf_b200.config import synthetic_ppo_config
+    from rlinf_b200.runner import EmbodiedRunner
+
+    B, T, obs, act = 256, 16, 8, 2
+    n = B * T
+    finals = []
+    for graphed in (False, True):
+        cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, update_epoch=2, num_minibatches=4,
+                                   micro_batch_size=n // 4 // accum, **{"actor.cuda_graph_update": graphed})
+        run = EmbodiedRunner(cfg)
+        ms = [run.run_iteration() for _ in range(3)]
+        torch.cuda.synchronize()
+        finals.append((run.actor.model.flat_params.cpu().clone(), ms[-1]))
+    torch.testing.assert_close(finals[0][0], finals[1][0], rtol=1e-4, atol=2e-5)
+    for k, v in finals[0][1].items():
+        if k != "critic/explained_variance" and np.isfinite(v):
+            assert abs(v - finals[1][1][k]) <= 1e-3 * abs(v) + 1e-5, k
+
+
 @pytest.mark.parametrize("accum", [1, 2])
 def test_update_matches_oracle_after_k_steps(accum):
     """Same rollout batch -> advantages -> shuffled mini/micro-batches -> k optimiser steps: parameters,
