@@ -18,6 +18,10 @@
 //   epilogue (warps 6-9, both CTAs): drain the own 128 TMEM lanes exactly as tc_gemm_kernel, then arrive on the
 //             LEADER's `tmem_empty` (8 arrivals).
 // Results are expected to be bit-identical to tc_gemm_kernel (same products, same k order, same accumulator).
+// Operand placement cross-checked against the CUTLASS/CuTe headers vendored in this image (cute/atom/mma_traits_sm100:
+// SM100_MMA_TF32_2x1SM_SS has ALayout 2 x (M/2, K), BLayout 2 x (N/2, K), CLayout 2 x (M/2, N); Allocator2Sm: the same
+// warp of BOTH CTAs issues tcgen05.alloc.cta_group::2; SM100_TMA_2SM_LOAD_2D: complete_tx on CTA 0's barrier;
+// umma_arrive_multicast_2x1SM: the multicast commit used below).
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "tma.cuh"
