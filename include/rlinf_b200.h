@@ -166,7 +166,9 @@ typedef struct rb200_ppo_args {
   int32_t critic_warmup;     /* 1: policy loss := 0 (no actor grads) */
   double entropy_bonus;      /* 0: none */
   double loss_scale;         /* 1/gradient_accumulation */
-  /* scratch: caller-provided, >= 32 doubles, contents ignored and overwritten */
+  /* scratch: caller-provided, 32 doubles, ZERO before its first use; every call leaves it zeroed again (the last CTA
+   * clears it), so one zero-initialised buffer per stream is reused without memset nodes. Calls sharing a workspace
+   * must be stream-ordered. */
   double* workspace;
   /* outputs */
   float* loss;        /* [1] total loss (after entropy bonus and loss_scale) */
@@ -177,6 +179,47 @@ typedef struct rb200_ppo_args {
 } rb200_ppo_args;
 
 int rb200_ppo_loss(const rb200_ppo_args* args, rb200_stream_t stream);
+
+/* "decoupled_actor_critic" (losses.py:27-167 + :315-380, registered :383-394): PPO clipped around a proximal policy.
+ * `base` carries everything shared with rb200_ppo_loss (entropy / log-ratio clamps / adv_stats must be unset);
+ * metrics use the RB200_DM_* layout. */
+enum {
+  RB200_DM_POLICY_LOSS = 0,            /* actor/policy_loss            */
+  RB200_DM_PROXIMAL_RATIO = 1,         /* actor/proximal_ratio         */
+  RB200_DM_CLIPPED_PROXIMAL_RATIO = 2, /* actor/clipped_proximal_ratio */
+  RB200_DM_CLIP_FRACTION = 3,          /* actor/clip_fraction          */
+  RB200_DM_DUAL_CLIP_FRACTION = 4,     /* actor/dual_clip_fraction     */
+  RB200_DM_BEHAV_CLIP_FRACTION = 5,    /* actor/behav_clip_fraction    */
+  RB200_DM_PROXIMAL_APPROX_KL = 6,     /* actor/proximal_approx_kl     */
+  RB200_DM_BEHAV_APPROX_KL = 7,        /* actor/behav_approx_kl        */
+  RB200_DM_VALUE_LOSS = 8,             /* critic/value_loss            */
+  RB200_DM_VALUE_CLIP_RATIO = 9,       /* critic/value_clip_ratio      */
+  RB200_DM_EV_COUNT = 10,              /* 10..14: explained-variance sufficient statistics, as RB200_M_EV_* */
+  RB200_DM_AVERAGE_VERSION = 15,       /* actor/average_version (valid iff slot 19 != 0) */
+  RB200_DM_TOTAL_LOSS = 16,
+  RB200_DM_TOKEN_NUM = 17,
+  RB200_DM_CURRENT_VERSION = 18,       /* actor/current_version */
+  RB200_DM_HAS_VERSION_METRICS = 19
+};
+typedef struct rb200_dppo_args {
+  rb200_ppo_args base;
+  const float* proximal_logprobs; /* [rows, C*A] or NULL: anchor = old_logprobs, or the version interpolation */
+  const float* versions;          /* [rows, C*A] fp32 weight version that generated each token, or NULL */
+  int32_t has_current_version;
+  double current_version;
+  int32_t has_behave_weight_threshold;
+  double behave_weight_threshold;
+} rb200_dppo_args;
+int rb200_decoupled_ppo_loss(const rb200_dppo_args* args, rb200_stream_t stream);
+
+/* "opd" (losses.py:427-505): loss = agg(-logprobs * stop_grad(advantages)) with the mask / mask_sum broadcast over the
+ * tokens of a unit. logprobs, advantages: [n_units, tokens_per_unit]; loss_mask (uint8), loss_mask_sum: [n_units].
+ * max_episode_steps > 0 selects masked_mean_ratio. workspace: as rb200_ppo_args.workspace. */
+enum { RB200_OM_POLICY_LOSS = 0, RB200_OM_OPD_REWARD = 1, RB200_OM_OPD_REVERSE_KL = 2, RB200_OM_TOTAL_LOSS = 16 };
+int rb200_opd_loss(const float* logprobs, const float* advantages, const uint8_t* loss_mask,
+                   const int64_t* loss_mask_sum, int64_t n_units, int tokens_per_unit, int max_episode_steps,
+                   double loss_scale, double* workspace, float* loss /*[1] or NULL*/,
+                   float* metrics /*[RB200_NUM_METRICS]*/, float* d_logprobs /*or NULL*/, rb200_stream_t stream);
 
 /* x[i] *= s (device scalar-free helper for autograd's upstream scalar). */
 int rb200_scale(float* x, int64_t n, float s, rb200_stream_t stream);
@@ -199,6 +242,17 @@ int rb200_adamw_step(float* params, const float* grads, float* exp_avg, float* e
                      int n_groups, double beta1, double beta2, double eps, double weight_decay,
                      float max_grad_norm, float grad_scale, const double* grad_sq /*[1]*/,
                      double* state /*[4]*/, rb200_stream_t stream);
+/* Same step with the per-group learning rates read from DEVICE memory (double[n_groups]) at execution time, so a
+ * captured CUDA graph follows an LR schedule (LambdaLR stepped once per run_training,
+ * workers/actor/embodied_fsdp_actor_worker.py:571, hybrid_engines/fsdp/utils.py:522) without re-capture.
+ * In both entries lr < 0 marks a FROZEN group: its parameters and moments are left untouched - what
+ * torch.optim.AdamW does for parameters outside its param groups (the actor during critic warm-up,
+ * fsdp_model_manager.py:523-531) or whose grad is None. */
+int rb200_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                         int64_t n, const int64_t* group_end_host, const double* group_lr_dev,
+                         int n_groups, double beta1, double beta2, double eps, double weight_decay,
+                         float max_grad_norm, float grad_scale, const double* grad_sq /*[1]*/,
+                         double* state /*[4]*/, rb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3/K5  MLP policy (3x256 tanh backbone + mean head, state-independent log-std, 3x256 value
@@ -342,6 +396,42 @@ int rb200_kl_penalty(const float* logprob, const float* ref_logprob, float* out,
  * out4 = {count, sum, min, max} of x[i] over entries with mask[i / mask_div] != 0 (mask NULL = all). */
 int rb200_masked_stats(const float* x, const uint8_t* mask, int64_t n, int64_t mask_div, double* out4,
                        rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f) rank 4 - the remaining advantage estimators of ADV_REGISTRY (rlinf/algorithms/advantages.py) and the
+ * fp64 masked normalisations of rlinf/utils/distributed.py (a24).  Step-major [L,B] tensors, uint8 0/1 masks.
+ * ---------------------------------------------------------------------------------------- */
+/* masked_stats (distributed.py:942-954) and the three sums masked_normalization all-reduces (:903-933):
+ * out3 = {count, sum x, sum x^2} over entries with mask != 0 (mask NULL = all), accumulated in fp64. */
+int rb200_masked_moments(const float* x, const uint8_t* mask, int64_t n, double* out3 /*reset by the call*/,
+                         rb200_stream_t stream);
+/* Apply half, stats3 = (all-reduced) {count, sum, sumsq}:
+ *  mode 0  masked_normalization(dim=None) :935-939  out = (x*mask - mean)/(sqrt(var[*n/(n-1)]) + eps), fp64 -> fp32
+ *  mode 1  normalize_from_stats :957-965            out = (x - mean) * rsqrt(max(var,0) + 1e-5)
+ *  mode 2  reinforce++ whitening, advantages.py:355-362   out = (x - mean) * rsqrt(max(var, eps)), biased var */
+int rb200_masked_normalize(const float* x, const uint8_t* mask, float* out, int64_t n, const double* stats3,
+                           int mode, double eps, int unbiased, rb200_stream_t stream);
+/* "raw", advantages.py:410-438: adv[l,b] = scores[b] * mask[l,b]; stats3 (nullable) = {n, sum, sumsq} of the valid
+ * entries for the optional safe_normalize-style normalisation (rb200_normalize, eps 1e-5). */
+int rb200_raw_advantages(const float* scores /*[B]*/, const uint8_t* loss_mask /*[L,B]*/, float* adv /*[L,B]*/,
+                         int L, int B, double* stats3, rb200_stream_t stream);
+/* "reinpp", advantages.py:302-364: reward at the reference's eos index (its fliplr quirk reproduced), optional
+ * -kl_beta * kl_penalty(logprob, ref_logprob) per token (kl_mode as rb200_kl_penalty), reverse cumulative sum over L
+ * (fp64 accumulation as torch's CPU cumsum); stats3 = masked {n, sum, sumsq} of the returns for mode-2 whitening. */
+int rb200_reinpp_returns(const float* rewards /*[B]*/, const uint8_t* loss_mask /*[L,B]*/, const float* logprob,
+                         const float* ref_logprob, float* ret /*[L,B]*/, int L, int B, double kl_beta, int kl_mode,
+                         double* stats3, rb200_stream_t stream);
+/* "grpo_video", advantages.py:124-164: mode 0 = "frame", 1 = "video"; the mask is float in the reference (plain
+ * product): pass it as mask_f32, or a 0/1 byte mask as mask_u8 (both NULL = no mask). */
+int rb200_grpo_video_advantages(const float* rewards /*[S,B]*/, const float* mask_f32, const uint8_t* mask_u8,
+                                float* adv /*[S,B]*/, int S, int B, int G, int mode, float eps, rb200_stream_t stream);
+/* "grpo_dynamic", advantages.py:167-299: per-turn advantages [n] from per-turn rewards and the turn -> trajectory map
+ * (int32, device); mode 0 = "trajectory", 1 = "turn".  The caller broadcasts over the sequence with the loss mask. */
+int rb200_grpo_dynamic_turn_advantages(const float* rewards /*[n]*/, const int32_t* idx_to_traj /*[n]*/,
+                                       float* turn_adv /*[n]*/, int n, int num_trajectories, int G, int mode,
+                                       float eps, rb200_stream_t stream);
+/* out = a - b, fp32 ("opd" advantages = teacher_logprobs - prev_logprobs, advantages.py:393). */
+int rb200_sub(const float* a, const float* b, float* out, int64_t n, rb200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -253,6 +253,72 @@ def reinpp_advantages(rewards, loss_mask, group_size, use_reinpp_baseline=False,
     return (ret - mean) * var.clamp(min=1e-8).rsqrt()
 
 
+def grpo_dynamic_advantages(rewards, loss_mask, group_size, idx_to_traj, advantage_mode="turn"):
+    """rlinf/algorithms/advantages.py:167-299 (compute_grpo_dynamic_advantages): GRPO per question over trajectory
+    rewards ("trajectory": mean of a trajectory's turn rewards, broadcast back to its turns) or over all turns of the
+    question ("turn"); unbiased std, eps 1e-6; broadcast over the sequence through the mask [seq_len, num_sequence]."""
+    n = len(idx_to_traj)
+    r = rewards.reshape(-1)
+    assert r.numel() == n
+    n_traj = max(idx_to_traj) + 1
+    assert n_traj % group_size == 0
+    turn_adv = torch.zeros(n, dtype=r.dtype)
+    if advantage_mode == "trajectory":
+        tot, cnt = torch.zeros(n_traj, dtype=r.dtype), torch.zeros(n_traj, dtype=torch.long)
+        for i, t in enumerate(idx_to_traj):
+            tot[t] += r[i]
+            cnt[t] += 1
+        per_traj = (tot / cnt.clamp(min=1).float()).view(-1, group_size)
+        norm = ((per_traj - per_traj.mean(-1, keepdim=True)) / (per_traj.std(-1, keepdim=True) + 1e-6)).view(-1)
+        for i, t in enumerate(idx_to_traj):
+            turn_adv[i] = norm[t]
+    elif advantage_mode == "turn":
+        question = torch.tensor([t // group_size for t in idx_to_traj])
+        for q in range(n_traj // group_size):
+            sel = question == q
+            x = r[sel]
+            turn_adv[sel] = (x - x.mean()) / (x.std() + 1e-6)
+    else:
+        raise ValueError(f"Invalid advantage_mode: {advantage_mode}. Must be 'trajectory' or 'turn'")
+    return (torch.zeros_like(loss_mask, dtype=r.dtype) + turn_adv.view(1, -1)) * loss_mask
+
+
+def masked_normalization(x, mask=None, unbiased=False, eps=1e-5, reduce=None):
+    """rlinf/utils/distributed.py:866-939 with dim=None: fp64; the input is multiplied by the mask first; `reduce`
+    stands for the three SUM all-reduces (a callable applied to the [factor, sum, sumsq] triple)."""
+    x = x.to(torch.float64).clone()
+    if mask is None:
+        factor = torch.tensor(float(x.numel()), dtype=torch.float64)
+    else:
+        m = mask.to(torch.float64)
+        x = x * m
+        factor = m.sum()
+    s, ss = x.sum(), x.square().sum()
+    if reduce is not None:
+        factor, s, ss = reduce(factor), reduce(s), reduce(ss)
+    mean = s / factor
+    var = ss / factor - mean**2
+    if unbiased:
+        var = var * factor / (factor - 1)
+    return ((x - mean) / (var.sqrt() + eps)).float()
+
+
+def masked_stats(x, mask=None):
+    """rlinf/utils/distributed.py:942-954."""
+    x = x.to(torch.float64)
+    x = x[mask.bool()] if mask is not None else x.reshape(-1)
+    return torch.tensor([x.numel(), x.sum(), x.square().sum()], dtype=torch.float64)
+
+
+def normalize_from_stats(x, stats):
+    """rlinf/utils/distributed.py:957-965."""
+    stats = stats.to(torch.float64)
+    count = stats[0].clamp_min(1.0)
+    mean = stats[1] / count
+    var = stats[2] / count - mean.square()
+    return ((x.to(torch.float64) - mean) * torch.rsqrt(var.clamp_min(0.0) + 1e-5)).float()
+
+
 def adv_and_returns_embodied(adv_type, rewards, dones, values=None, loss_mask=None,
                              loss_mask_sum=None, gamma=1.0, gae_lambda=1.0, group_size=8,
                              reward_type="action_level", **kw):
@@ -718,17 +784,60 @@ def mlp_sample(params, states, noise):
 # --------------------------------------------------------------------------
 
 
-def build_adamw(params: dict, lr, value_lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+def build_adamw(params: dict, lr, value_lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                enable_critic_warmup=False):
+    """build_optimizer (fsdp_model_manager.py:501-590). enable_critic_warmup: only the value-head parameters are
+    optimised, everything else is frozen (:523-531)."""
     actor = [p for n, p in params.items() if "value_head" not in n]
     critic = [p for n, p in params.items() if "value_head" in n]
-    groups = [{"params": actor, "lr": lr, "betas": betas}]
+    groups = []
+    if enable_critic_warmup:
+        for p in actor:
+            p.requires_grad_(False)
+    else:
+        for p in params.values():
+            p.requires_grad_(True)
+        groups.append({"params": actor, "lr": lr, "betas": betas})
     if critic:
         groups.append({"params": critic, "lr": value_lr, "betas": betas})
     return torch.optim.AdamW(groups, eps=eps, weight_decay=weight_decay)
 
 
+def lr_lambda(optim_cfg: dict, base_lr: float):
+    """build_lr_scheduler + get_lr_scheduler (fsdp_model_manager.py:465-499, fsdp/utils.py:522-604): the LambdaLR
+    multiplier as a function of the scheduler step (constant / cosine / openpi_cosine)."""
+    g = optim_cfg.get
+    total = g("total_training_steps", 0)
+    warm = int(g("lr_warmup_steps", -1))
+    if warm < 0:
+        warm = int(g("lr_warmup_steps_ratio", 0.0) * total)
+    kind = g("lr_scheduler", "constant")
+    cycles = g("num_cycles", 0.5)
+    min_lr, min_lr_rate = g("min_lr", 0.0), g("min_lr_rate", None)
+
+    def constant(s):
+        return float(s) / float(max(1.0, warm)) if s < warm else 1.0
+
+    def cosine(s):
+        rate = min_lr_rate if min_lr_rate is not None else min_lr / base_lr
+        if s < warm:
+            return float(s) / float(max(1, warm))
+        progress = float(s - warm) / float(max(1, total - warm))
+        return max(0, 0.5 * (1.0 + math.cos(math.pi * float(cycles) * 2.0 * progress)) * (1 - rate) + rate)
+
+    def openpi(s):
+        mm = min_lr_rate if min_lr_rate is not None else (min_lr / base_lr if (min_lr and base_lr > 0) else 0.0)
+        if s < warm:
+            init = 1.0 / (warm + 1)
+            return init + (1.0 - init) * s / max(1, warm)
+        progress = min(1.0, (s - warm) / max(1, total - warm))
+        return mm + (1.0 - mm) * 0.5 * (1.0 + math.cos(math.pi * progress))
+
+    return {"constant": constant, "cosine": cosine, "openpi_cosine": openpi, "ref_warmup_cosine": openpi}[kind]
+
+
 def optimizer_step(optimizer, params: dict, clip_grad):
-    gn = torch.nn.utils.clip_grad_norm_(list(params.values()), clip_grad)
+    gn = torch.nn.utils.clip_grad_norm_([p for p in params.values() if p.grad is not None], clip_grad)
     if torch.isfinite(gn):
         optimizer.step()
     return float(gn)

@@ -81,15 +81,37 @@ class RunnerOracle:
         for p in self.params.values():
             p.requires_grad_(True)
         o = cfg["actor"]["optim"]
-        self.opt = O.build_adamw(self.params, o["lr"], o.get("value_lr", o["lr"]),
-                                 (o.get("adam_beta1", 0.9), o.get("adam_beta2", 0.999)), o.get("adam_eps", 1e-8),
-                                 o.get("weight_decay", 1e-2))
+        self.optimizer_steps = 0
+        self.critic_warmup_steps = int(o.get("critic_warmup_steps", 0) or 0)  # fsdp_model_manager.py:88-93
+        self.opt = self._build_optimizer(self.critic_warmup_steps > 0)
+        self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, O.lr_lambda(o, o["lr"]))
         self.env = SyntheticEnvCPU(self.B, self.obs_dim, self.act_dim, et["max_episode_steps"], et["auto_reset"],
                                    et.get("p_term", 0.005), et.get("noise_std", 0.1),
                                    et.get("reward_noise_std", 0.01), et.get("seed", 1234))
         self.gen = torch.Generator().manual_seed(cfg["actor"]["seed"])
         self.obs = None
         self.timers = {}
+
+    def _build_optimizer(self, warmup):
+        o = self.cfg["actor"]["optim"]
+        return O.build_adamw(self.params, o["lr"], o.get("value_lr", o["lr"]),
+                             (o.get("adam_beta1", 0.9), o.get("adam_beta2", 0.999)), o.get("adam_eps", 1e-8),
+                             o.get("weight_decay", 1e-2), enable_critic_warmup=warmup)
+
+    def _optimizer_step(self):
+        """FSDPModelManager.optimizer_step (fsdp_model_manager.py:429-463)."""
+        self.optimizer_steps += 1
+        gn = O.optimizer_step(self.opt, self.params, self.cfg["actor"]["optim"]["clip_grad"])
+        if self.critic_warmup_steps > 0:
+            lr_list = [0.0 for _ in self.opt.param_groups]
+            if self.optimizer_steps >= self.critic_warmup_steps:
+                self.opt = self._build_optimizer(False)
+                self.critic_warmup_steps = 0
+                o = self.cfg["actor"]["optim"]
+                self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, O.lr_lambda(o, o["lr"]))
+        else:
+            lr_list = [g["lr"] for g in self.opt.param_groups]
+        return gn, lr_list
 
     # -- rollout (env_worker.py:1059-1349 / huggingface_worker.py:678-781) -----------------------------
     @torch.no_grad()
@@ -98,7 +120,7 @@ class RunnerOracle:
         a = self.cfg["algorithm"]
         gamma, boot_always = a.get("gamma", 1), a.get("bootstrap_type", "standard") != "standard"
         B, T = self.B, self.T
-        if self.obs is None:
+        if self.obs is None or not self.env.auto_reset:  # bootstrap_step, env_worker.py:908-935
             self.obs, _ = self.env.reset()
         lists = {k: [] for k in ("rewards", "dones", "terminations", "truncations", "prev_values", "prev_logprobs",
                                  "states", "action")}
@@ -139,60 +161,56 @@ class RunnerOracle:
         return batch
 
     # -- advantages + update ---------------------------------------------------------------------------
-    def update(self, batch, rank=0, world_size=1):
+    def _prepare(self, batch, rank=0):
+        """recv_rollout_trajectories + compute_advantages_and_returns + the seeded shuffle of run_training."""
         cfg, a = self.cfg, self.cfg["algorithm"]
-        t0 = time.perf_counter()
+        E = cfg["env"]["train"].get("rollout_epoch", 1)
+        if E != 1:
+            batch = O.merge_rollout_epochs(batch, E)
         if not cfg["env"]["train"]["auto_reset"] and not cfg["env"]["train"].get("ignore_terminations", False):
             batch["loss_mask"], batch["loss_mask_sum"] = O.loss_mask_from_dones(batch["dones"])
         res = O.adv_and_returns_embodied(a["adv_type"], batch["rewards"], batch["dones"], batch.get("prev_values"),
                                          batch.get("loss_mask"), batch.get("loss_mask_sum"), a.get("gamma", 1),
                                          a.get("gae_lambda", 1), a.get("group_size", 8), a["reward_type"])
         batch.update(res)
-        t1 = time.perf_counter()
         n = batch["prev_logprobs"].shape[0] * batch["prev_logprobs"].shape[1]
         perm = O.shuffle_indices(n, cfg["actor"]["seed"] + rank)
         with torch.no_grad():
-            flat = O.flatten_and_shuffle(batch, perm)
-        per_rank = cfg["actor"]["global_batch_size"] // world_size
-        mbs = cfg["actor"]["micro_batch_size"]
-        accum = per_rank // mbs
+            return O.flatten_and_shuffle(batch, perm), n
+
+    def _micro_loss(self, flat, sl, accum, metrics):
+        """train_micro_batch (embodied_fsdp_actor_worker.py:591-699): returns the loss to call .backward() on."""
+        cfg, a = self.cfg, self.cfg["algorithm"]
         with_critic = a["adv_type"] == "gae"
         A = cfg["actor"]["model"]["action_dim"]
         ent_bonus = a.get("entropy_bonus", 0) or 0
-        metrics = {}
-        for _ in range(a.get("update_epoch", 1)):
-            for gb in range(n // per_rank):
-                self.opt.zero_grad()
-                for k in range(accum):
-                    lo = gb * per_rank + k * mbs
-                    sl = slice(lo, lo + mbs)
-                    out = O.mlp_forward(self.params, flat["forward_inputs"]["states"][sl],
-                                        flat["forward_inputs"]["action"][sl], want_entropy=ent_bonus > 0,
-                                        want_values=with_critic)
-                    loss, md = O.policy_loss_embodied(
-                        a["loss_type"], out["logprobs"], flat["prev_logprobs"][sl], flat["advantages"][sl],
-                        a["logprob_type"], A, loss_mask=None if flat.get("loss_mask") is None else flat["loss_mask"][sl],
-                        loss_mask_sum=None if flat.get("loss_mask_sum") is None else flat["loss_mask_sum"][sl],
-                        values=out.get("values") if with_critic else None,
-                        prev_values=flat["prev_values"][sl] if with_critic else None,
-                        returns=flat["returns"][sl] if with_critic else None, reward_type=a["reward_type"],
-                        clip_ratio_low=a["clip_ratio_low"], clip_ratio_high=a["clip_ratio_high"],
-                        value_clip=a.get("value_clip"), huber_delta=a.get("huber_delta"),
-                        max_episode_steps=cfg["env"]["train"]["max_episode_steps"] if flat.get("loss_mask_sum") is not None else None)
-                    if ent_bonus > 0:
-                        ent = O.entropy_term(out["entropy"], a["entropy_type"], A, out["logprobs"].shape[0],
-                                             None if flat.get("loss_mask") is None else flat["loss_mask"][sl])
-                        loss = loss - ent_bonus * ent
-                        md["actor/entropy_loss"] = float(ent.detach())
-                    loss = loss / accum
-                    loss.backward()
-                    md["actor/total_loss"] = float(loss.detach())
-                    for kk, vv in md.items():
-                        metrics.setdefault(kk, []).append(vv)
-                gn = O.optimizer_step(self.opt, self.params, cfg["actor"]["optim"]["clip_grad"])
-                metrics.setdefault("actor/grad_norm", []).append(gn)
-        t2 = time.perf_counter()
-        self.timers = {"adv_s": t1 - t0, "train_s": t2 - t1}
+        warm = self.optimizer_steps < self.critic_warmup_steps
+        out = O.mlp_forward(self.params, flat["forward_inputs"]["states"][sl], flat["forward_inputs"]["action"][sl],
+                            want_entropy=ent_bonus > 0, want_values=with_critic)
+        loss, md = O.policy_loss_embodied(
+            a["loss_type"], out["logprobs"], flat["prev_logprobs"][sl], flat["advantages"][sl],
+            a["logprob_type"], A, loss_mask=None if flat.get("loss_mask") is None else flat["loss_mask"][sl],
+            loss_mask_sum=None if flat.get("loss_mask_sum") is None else flat["loss_mask_sum"][sl],
+            values=out.get("values") if with_critic else None,
+            prev_values=flat["prev_values"][sl] if with_critic else None,
+            returns=flat["returns"][sl] if with_critic else None, reward_type=a["reward_type"],
+            clip_ratio_low=a["clip_ratio_low"], clip_ratio_high=a["clip_ratio_high"],
+            value_clip=a.get("value_clip"), huber_delta=a.get("huber_delta"),
+            max_episode_steps=cfg["env"]["train"]["max_episode_steps"] if flat.get("loss_mask_sum") is not None else None,
+            critic_warmup=warm)
+        md["actor/entropy_loss"] = 0.0
+        if ent_bonus > 0 and not warm:
+            ent = O.entropy_term(out["entropy"], a["entropy_type"], A, out["logprobs"].shape[0],
+                                 None if flat.get("loss_mask") is None else flat["loss_mask"][sl])
+            loss = loss - ent_bonus * ent
+            md["actor/entropy_loss"] = float(ent.detach())
+        loss = loss / accum
+        md["actor/total_loss"] = float(loss.detach())
+        for kk, vv in md.items():
+            metrics.setdefault(kk, []).append(vv)
+        return loss
+
+    def _finish_metrics(self, metrics):
         ev = {k: sum(v) for k, v in metrics.items() if k.startswith(O.EV_PREFIX)}
         out = {k: sum(v) / len(v) for k, v in metrics.items() if not k.startswith(O.EV_PREFIX)}
         if ev:
@@ -201,6 +219,46 @@ class RunnerOracle:
             ec = ev[O.EV_PREFIX + "errors_sq_sum"] - ev[O.EV_PREFIX + "errors_sum"] ** 2 / max(cnt, 1)
             out["critic/explained_variance"] = (1 - ec / rc) if (cnt >= 2 and rc != 0) else float("nan")
         return out
+
+    def update(self, batch, rank=0, world_size=1):
+        """One rank's view of run_training (gradients of THIS rank only; see update_dp for the data-parallel average)."""
+        return self.update_dp([batch], ranks=[rank], world_size=world_size)
+
+    def update_dp(self, batches, ranks=None, world_size=None):
+        """Data-parallel run_training emulated in one process: every rank holds the same parameters, shuffles its own
+        shard with seed+rank (embodied_fsdp_actor_worker.py:511-513), and the gradients of one optimiser step are the
+        MEAN over ranks (FSDP/DDP gradient averaging) - here: sum of the per-rank backward passes / number of ranks."""
+        cfg, a = self.cfg, self.cfg["algorithm"]
+        ranks = list(range(len(batches))) if ranks is None else ranks
+        world_size = world_size or len(batches)
+        t0 = time.perf_counter()
+        prepared = [self._prepare(b, r) for b, r in zip(batches, ranks)]
+        t1 = time.perf_counter()
+        n = prepared[0][1]
+        per_rank = cfg["actor"]["global_batch_size"] // world_size
+        mbs = cfg["actor"]["micro_batch_size"]
+        accum = per_rank // mbs
+        metrics = {}
+        for _ in range(a.get("update_epoch", 1)):
+            for gb in range(n // per_rank):
+                self.opt.zero_grad()
+                for flat, _n in prepared:
+                    for k in range(accum):
+                        lo = gb * per_rank + k * mbs
+                        self._micro_loss(flat, slice(lo, lo + mbs), accum, metrics).backward()
+                if len(prepared) > 1:
+                    for p in self.params.values():
+                        if p.grad is not None:
+                            p.grad.div_(len(prepared))
+                gn, lr_list = self._optimizer_step()
+                metrics.setdefault("actor/grad_norm", []).append(gn)
+                metrics.setdefault("actor/lr", []).append(lr_list[0])
+                if len(lr_list) > 1:
+                    metrics.setdefault("critic/lr", []).append(lr_list[1])
+        self.sched.step()
+        t2 = time.perf_counter()
+        self.timers = {"adv_s": t1 - t0, "train_s": t2 - t1}
+        return self._finish_metrics(metrics)
 
     def run_iteration(self):
         t0 = time.perf_counter()

@@ -55,6 +55,22 @@ class PpoArgs(C.Structure):
     ]
 
 
+class DppoArgs(C.Structure):
+    _fields_ = [("base", PpoArgs), ("proximal_logprobs", c_void_p), ("versions", c_void_p),
+                ("has_current_version", C.c_int32), ("current_version", c_double),
+                ("has_behave_weight_threshold", C.c_int32), ("behave_weight_threshold", c_double)]
+
+
+DM_KEYS = {
+    0: "actor/policy_loss", 1: "actor/proximal_ratio", 2: "actor/clipped_proximal_ratio", 3: "actor/clip_fraction",
+    4: "actor/dual_clip_fraction", 5: "actor/behav_clip_fraction", 6: "actor/proximal_approx_kl",
+    7: "actor/behav_approx_kl", 8: "critic/value_loss", 9: "critic/value_clip_ratio",
+    10: "__sum__/_critic_explained_variance/count", 11: "__sum__/_critic_explained_variance/returns_sum",
+    12: "__sum__/_critic_explained_variance/returns_sq_sum", 13: "__sum__/_critic_explained_variance/errors_sum",
+    14: "__sum__/_critic_explained_variance/errors_sq_sum",
+}
+
+
 class MlpLayout(C.Structure):
     _fields_ = [
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("value_dim", C.c_int32), ("hidden", C.c_int32),
@@ -79,12 +95,17 @@ SIGNATURES = {
     "rb200_grpo_advantages": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "rb200_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "rb200_ppo_loss": (c_int, [C.POINTER(PpoArgs), c_void_p]),
+    "rb200_decoupled_ppo_loss": (c_int, [C.POINTER(DppoArgs), c_void_p]),
+    "rb200_opd_loss": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_double] + [c_void_p] * 5),
     "rb200_scale": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "rb200_scale_by": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "rb200_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "rb200_adamw_step": (c_int, [c_void_p] * 4 + [c_int64, C.POINTER(c_int64), C.POINTER(c_double), c_int,
                                                   c_double, c_double, c_double, c_double, c_float, c_float,
                                                   c_void_p, c_void_p, c_void_p]),
+    "rb200_adamw_step_dev": (c_int, [c_void_p] * 4 + [c_int64, C.POINTER(c_int64), c_void_p, c_int,
+                                                      c_double, c_double, c_double, c_double, c_float, c_float,
+                                                      c_void_p, c_void_p, c_void_p]),
     "rb200_mlp_layout_init": (c_int, [C.POINTER(MlpLayout), c_int, c_int, c_int, c_int]),
     "rb200_mlp_fwd_scratch_floats": (c_int64, [C.POINTER(MlpLayout), c_int64]),
     "rb200_mlp_wsplit_floats": (c_int64, [C.POINTER(MlpLayout)]),
@@ -108,6 +129,13 @@ SIGNATURES = {
     "rb200_kl_penalty": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_void_p]),
     "rb200_masked_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "rb200_counter_add": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "rb200_masked_moments": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rb200_masked_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_double, c_int, c_void_p]),
+    "rb200_raw_advantages": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rb200_reinpp_returns": (c_int, [c_void_p] * 5 + [c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
+    "rb200_grpo_video_advantages": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "rb200_grpo_dynamic_turn_advantages": (c_int, [c_void_p] * 3 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "rb200_sub": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _LIB: Optional[C.CDLL] = None

@@ -2,7 +2,8 @@
 
 Importing the package fills the registries, like rlinf/algorithms/__init__.py:16.
 """
-from . import advantages, losses  # noqa: F401  (registration side effects)
+from . import advantages, loss_scales, losses  # noqa: F401  (registration side effects)
+from .loss_scales import LOSS_SCALE_REGISTRY, get_loss_scales, register_loss_scale  # noqa: F401
 from .registry import (  # noqa: F401
     ADV_REGISTRY,
     LOSS_REGISTRY,

@@ -26,6 +26,7 @@ class _FusedPpoLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logprobs, values, entropy, cfg):
+        cfg = dict(cfg)
         loss, metrics, d_lp, d_v, d_e = ops.ppo_loss(
             logprobs=logprobs.detach(), values=None if values is None else values.detach(),
             entropy=None if entropy is None else entropy.detach(), want_grads=True, **cfg)
@@ -62,6 +63,71 @@ def _metrics_dict(metrics: torch.Tensor, with_critic: bool, as_float: bool) -> d
     return {L.M_KEYS[s]: metrics[s] for s in slots}
 
 
+def _decoupled_metrics_dict(metrics: torch.Tensor, as_float: bool) -> dict:
+    host = metrics.tolist() if as_float else None
+    get = (lambda s: host[s]) if as_float else (lambda s: metrics[s])
+    out = {k: get(s) for s, k in L.DM_KEYS.items()}
+    has_ver = (host[19] if as_float else float(metrics[19])) != 0
+    if has_ver:
+        out["actor/average_version"] = get(15)
+        out["actor/current_version"] = get(18)
+    return out
+
+
+def preprocess_loss_inputs(logprobs, old_logprobs, advantages, logprob_type=None, single_action_dim=None,
+                           loss_mask=None, loss_mask_sum=None, values=None, prev_values=None, returns=None,
+                           reward_type=None, versions=None, **kwargs) -> dict:
+    """rlinf/algorithms/utils.py:280-376 for loss functions a USER registers (the built-in entries never come here:
+    their reduction happens inside the fused kernels).  Layout work only - reshapes, the per-action / per-chunk sums
+    that carry autograd history, trailing-dimension expansion."""
+    def flat(t):
+        return None if t is None else t.flatten()
+
+    def rank_up(t, shape):
+        if t is None:
+            return None
+        while t.dim() < len(shape) and t.shape != shape:
+            t = t.unsqueeze(-1)
+        return t
+
+    if reward_type == "chunk_level":
+        advantages, loss_mask, loss_mask_sum = flat(advantages), flat(loss_mask), flat(loss_mask_sum)
+        values, prev_values, returns = flat(values), flat(prev_values), flat(returns)
+    bsz = logprobs.shape[0]
+    proximal = kwargs.get("proximal_logprobs", None)
+    A = single_action_dim
+
+    def per(t):
+        return None if t is None else t.reshape(bsz, -1, A)
+
+    if logprob_type == "token_level":
+        logprobs, old_logprobs, proximal, versions = per(logprobs), per(old_logprobs), per(proximal), per(versions)
+        if kwargs.get("loss_type") == "opd":
+            assert advantages.shape == logprobs.shape, (
+                f"OPD advantages shape {advantages.shape} must match logprobs shape {logprobs.shape}.")
+        else:
+            advantages = advantages.unsqueeze(-1)
+        loss_mask = None if loss_mask is None else loss_mask.unsqueeze(-1)
+        loss_mask_sum = None if loss_mask_sum is None else loss_mask_sum.unsqueeze(-1)
+    elif logprob_type == "action_level":
+        logprobs, old_logprobs = per(logprobs).sum(dim=-1), per(old_logprobs).sum(dim=-1)
+        proximal = None if proximal is None else per(proximal).sum(dim=-1)
+        versions = None if versions is None else per(versions)[..., 0]
+    elif logprob_type == "chunk_level":
+        logprobs, old_logprobs = per(logprobs).sum(dim=[1, 2]), per(old_logprobs).sum(dim=[1, 2])
+        proximal = None if proximal is None else per(proximal).sum(dim=[1, 2])
+        versions = None if versions is None else per(versions)[:, 0, 0]
+    shape = logprobs.shape
+    kwargs.update({
+        "logprobs": logprobs, "old_logprobs": old_logprobs, "proximal_logprobs": proximal,
+        "versions": rank_up(versions, shape), "advantages": rank_up(advantages, shape),
+        "loss_mask": rank_up(loss_mask, shape), "loss_mask_sum": rank_up(loss_mask_sum, shape),
+        "values": rank_up(values, shape), "prev_values": rank_up(prev_values, shape), "returns": rank_up(returns, shape),
+        "logprob_type": logprob_type, "single_action_dim": single_action_dim, "reward_type": reward_type,
+    })
+    return kwargs
+
+
 def postprocess_loss_metric(metrics_data: dict) -> dict:
     """rlinf/algorithms/utils.py:379-385."""
     for k, v in metrics_data.items():
@@ -70,15 +136,18 @@ def postprocess_loss_metric(metrics_data: dict) -> dict:
     return metrics_data
 
 
-def _run(logprobs, values, entropy, cfg, with_critic, as_float):
+def _run(logprobs, values, entropy, cfg, with_critic, as_float, decoupled=False):
     needs_grad = torch.is_grad_enabled() and (
-        logprobs.requires_grad or (values is not None and values.requires_grad))
+        logprobs.requires_grad or (values is not None and values.requires_grad)
+        or (entropy is not None and entropy.requires_grad))
     if needs_grad:
         loss, metrics = _FusedPpoLoss.apply(logprobs, values, entropy, cfg)
     else:
         loss, metrics, *_ = ops.ppo_loss(logprobs=logprobs.detach(), values=None if values is None else values.detach(),
                                          entropy=entropy, want_grads=False, **cfg)
         loss = loss.reshape(())
+    if decoupled:
+        return loss, _decoupled_metrics_dict(metrics, as_float), metrics
     return loss, _metrics_dict(metrics, with_critic, as_float), metrics
 
 
@@ -90,7 +159,8 @@ def fused_embodied_policy_loss(**kwargs):
     logprobs = kwargs["logprobs"]
     dev = logprobs.device if logprobs.is_cuda else L.default_device()
     logprobs = logprobs if logprobs.is_cuda else logprobs.to(dev)
-    with_critic = loss_type == "actor_critic"
+    decoupled = loss_type == "decoupled_actor_critic"
+    with_critic = loss_type in ("actor_critic", "decoupled_actor_critic")
     values = kwargs.get("values") if with_critic else None
     _check_fp32(logprobs=logprobs, old_logprobs=kwargs["old_logprobs"], advantages=kwargs["advantages"])
     A = int(kwargs.get("single_action_dim") or logprobs.shape[-1])
@@ -130,8 +200,44 @@ def fused_embodied_policy_loss(**kwargs):
         values = values if values.is_cuda else values.to(dev)
         _check_v = per_unit(values.detach(), "values")  # shape check only
         del _check_v
-    loss, metrics, _ = _run(logprobs.reshape(bsz, Cc * A), None if values is None else values.reshape(bsz, U), None,
-                            cfg, with_critic, as_float=True)
+    # Extension kwargs (absent in the reference's call, where the WORKER subtracts the entropy bonus and divides by the
+    # gradient accumulation after policy_loss returns - embodied_fsdp_actor_worker.py:678-695): when given, both are
+    # folded into the same fused launch and `actor/entropy_loss` / `actor/total_loss` are reported.
+    if decoupled:
+        def full(t, name):
+            if t is None:
+                return None
+            t = L.to_device(t, dev, torch.float32)
+            if t.numel() != bsz * Cc * A:
+                raise RuntimeError(f"{name} has {t.numel()} entries, expected {bsz * Cc * A}")
+            return t.reshape(bsz, Cc * A)
+
+        cfg["_decoupled"] = dict(proximal_logprobs=full(kwargs.get("proximal_logprobs"), "proximal_logprobs"),
+                                 versions=full(kwargs.get("versions"), "versions"),
+                                 current_version=kwargs.get("current_version"),
+                                 behave_weight_threshold=kwargs.get("behave_weight_threshold"))
+        for k in ("clip_log_ratio_min", "clip_log_ratio_max"):
+            cfg.pop(k, None)  # compute_decoupled_ppo_actor_loss has no log-ratio clamps (they fall into **kwargs)
+    entropy = kwargs.get("entropy")
+    ent_bonus = float(kwargs.get("entropy_bonus", 0.0) or 0.0)
+    if entropy is not None:
+        if decoupled:
+            raise NotImplementedError("entropy term is not fused into the decoupled loss kernel")
+        ent_type = kwargs.get("entropy_type", "action_level")
+        want = "chunk_level" if logprob_type == "chunk_level" else "action_level"
+        if ent_type != want:
+            raise NotImplementedError(f"entropy_type={ent_type!r} with logprob_type={logprob_type!r}: the fused kernel "
+                                      f"reduces the entropy over the same unit as the log-probs ({want})")
+        entropy = (entropy if entropy.is_cuda else entropy.to(dev)).reshape(bsz, Cc * A)
+        cfg["entropy_bonus"] = ent_bonus
+    if kwargs.get("loss_scale") is not None:
+        cfg["loss_scale"] = float(kwargs["loss_scale"])
+    loss, metrics, raw = _run(logprobs.reshape(bsz, Cc * A), None if values is None else values.reshape(bsz, U), entropy,
+                              cfg, with_critic, as_float=True, decoupled=decoupled)
+    if entropy is not None or kwargs.get("loss_scale") is not None:
+        host = raw.tolist()
+        metrics["actor/entropy_loss"] = host[15]
+        metrics["actor/total_loss"] = host[16]
     return loss, metrics
 
 
@@ -192,3 +298,98 @@ def compute_grpo_actor_loss_fn(**kwargs) -> tuple[torch.Tensor, dict]:
 def compute_ppo_actor_loss(**kwargs):
     """losses.py:170-312 - same kernel, actor half only."""
     return compute_grpo_actor_loss_fn(**kwargs)
+
+
+@register_policy_loss("decoupled_actor_critic")
+def compute_decoupled_ppo_actor_critic_loss(**kwargs) -> tuple[torch.Tensor, dict]:
+    """Decoupled PPO actor + critic loss (losses.py:27-167, 383-394) on preprocess_loss_inputs kwargs."""
+    lp, v, cfg = _from_preprocessed(kwargs, True)
+    n_units, g = lp.shape
+
+    def elem(t):
+        if t is None:
+            return None
+        t = L.to_device(t, lp.device, torch.float32)
+        if t.numel() == n_units * g:
+            return t.reshape(n_units, g)
+        if g == 1 or t.numel() != n_units:
+            raise RuntimeError(f"cannot match a tensor of {t.numel()} entries to {n_units} x {g} log-probs")
+        return t.reshape(n_units, 1).expand(n_units, g).contiguous()
+
+    cfg["_decoupled"] = dict(proximal_logprobs=elem(kwargs.get("proximal_logprobs")), versions=elem(kwargs.get("versions")),
+                             current_version=kwargs.get("current_version"),
+                             behave_weight_threshold=kwargs.get("behave_weight_threshold"))
+    for k in ("clip_log_ratio_min", "clip_log_ratio_max"):
+        cfg.pop(k, None)
+    loss, metrics, _ = _run(lp, v, None, cfg, True, as_float=False, decoupled=True)
+    return loss, metrics
+
+
+class _FusedOpdLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logprobs, cfg):
+        loss, metrics, d_lp = ops.opd_loss(logprobs=logprobs.detach(), want_grads=True, **cfg)
+        ctx.grad = d_lp
+        ctx.shape = logprobs.shape
+        ctx.mark_non_differentiable(metrics)
+        return loss.reshape(()), metrics
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_metrics):
+        g, ctx.grad = ctx.grad, None
+        return ops.scale_by_(g, g_loss).view(ctx.shape), None
+
+
+@register_policy_loss("opd")
+def compute_opd_actor_loss(logprobs: torch.Tensor, advantages: torch.Tensor, loss_mask: Optional[torch.Tensor] = None,
+                           loss_agg_func=None, max_episode_steps: Optional[int] = None,
+                           loss_mask_sum: Optional[torch.Tensor] = None, **kwargs) -> tuple[torch.Tensor, dict]:
+    """VLA-OPD actor loss with stop-gradient dense rewards (losses.py:427-505): agg(-logprobs * advantages)."""
+    _check_fp32(logprobs=logprobs, advantages=advantages)
+    assert advantages.shape == logprobs.shape, (
+        f"OPD advantages shape {advantages.shape} must match logprobs shape {logprobs.shape}.")
+    assert loss_mask is not None, "OPD actor loss requires loss_mask."
+    assert loss_mask_sum is not None, "OPD actor loss requires loss_mask_sum."
+    dev = logprobs.device if logprobs.is_cuda else L.default_device()
+    lp = logprobs if logprobs.is_cuda else logprobs.to(dev)
+    tok = lp.shape[-1]
+    n_units = lp.numel() // tok
+
+    def unit(t, name):
+        t = L.to_device(t, dev)
+        if t.dim() == lp.dim() - 1:
+            t = t.unsqueeze(-1)
+        assert t.dim() == lp.dim(), f"OPD {name} rank {t.dim()} must match logprobs rank {lp.dim()}."
+        assert t.shape[:-1] == lp.shape[:-1], (
+            f"OPD {name} shape {t.shape} must match logprobs shape {lp.shape} except the token dimension.")
+        if t.shape[-1] != 1:
+            assert t.shape[-1] == tok, (
+                f"OPD {name} token dimension {t.shape[-1]} must be 1 or match logprobs token dimension {tok}.")
+            # a per-token mask: one unit per token
+            return t.reshape(-1), True
+        return t.reshape(n_units), False
+
+    m, m_tok = unit(loss_mask, "loss_mask")
+    ms, ms_tok = unit(loss_mask_sum, "loss_mask_sum")
+    if m_tok != ms_tok:  # bring both to per-token granularity
+        if not m_tok:
+            m = m.reshape(n_units, 1).expand(n_units, tok).reshape(-1)
+        if not ms_tok:
+            ms = ms.reshape(n_units, 1).expand(n_units, tok).reshape(-1)
+        m_tok = True
+    lp2 = lp.reshape(-1, 1) if m_tok else lp.reshape(n_units, tok)
+    cfg = dict(advantages=L.to_device(advantages, dev, torch.float32).reshape(lp2.shape), loss_mask=m, loss_mask_sum=ms,
+               max_episode_steps=max_episode_steps)
+    if torch.is_grad_enabled() and logprobs.requires_grad:
+        loss, metrics = _FusedOpdLoss.apply(lp2, cfg)
+    else:
+        loss, metrics, _ = ops.opd_loss(logprobs=lp2.detach(), want_grads=False, **cfg)
+        loss = loss.reshape(())
+    return loss, {"actor/policy_loss": metrics[0], "actor/opd_reward": metrics[1], "actor/opd_reverse_kl": metrics[2]}
+
+
+# built-in entries: for task_type == "embodied" registry.policy_loss hands them the RAW worker kwargs through this marker
+# (one fused launch group); a callable a user registers under the same name has no marker and takes the generic route
+compute_ppo_actor_critic_loss._rb200_fused_embodied = fused_embodied_policy_loss
+compute_grpo_actor_loss_fn._rb200_fused_embodied = fused_embodied_policy_loss
+compute_decoupled_ppo_actor_critic_loss._rb200_fused_embodied = fused_embodied_policy_loss

@@ -69,10 +69,14 @@ def policy_loss(**kwargs) -> tuple[torch.Tensor, dict]:
     loss_type = kwargs["loss_type"]
     get_policy_loss(loss_type)  # same "not registered" error
     task_type = kwargs["task_type"]
-    if task_type == "embodied" and loss_type in ("actor_critic", "actor") and LOSS_REGISTRY[loss_type] in (
-            losses.compute_ppo_actor_critic_loss, losses.compute_grpo_actor_loss_fn):
-        return losses.fused_embodied_policy_loss(**kwargs)
     loss_fn = LOSS_REGISTRY[loss_type]
+    # Built-in entries carry a marker: for them the embodied chain preprocess -> loss -> backward is ONE fused launch
+    # group. A callable a user registered under the same name has no marker and takes the reference's generic route.
+    fused = getattr(loss_fn, "_rb200_fused_embodied", None)
+    if task_type == "embodied" and fused is not None:
+        return fused(**kwargs)
+    if task_type == "embodied":
+        kwargs = losses.preprocess_loss_inputs(**kwargs)
     loss, metrics_data = loss_fn(**kwargs)
     if task_type == "embodied":
         metrics_data = losses.postprocess_loss_metric(metrics_data)
@@ -85,6 +89,12 @@ def calculate_adv_and_returns(**kwargs):
     fn = get_adv_and_returns(adv_type)
     task_type = kwargs["task_type"]
     if task_type == "embodied":
+        if adv_type == "opd":  # registry.py:106-110: no layout pre/post-processing for the dense OPD rewards
+            advantages, returns = fn(**kwargs)
+            res = {"advantages": advantages}
+            if returns is not None:
+                res["returns"] = returns
+            return res
         kwargs = preprocess_embodied_advantages_inputs(**kwargs)
         if adv_type not in ("gae", "grpo_video"):
             kwargs = calculate_scores(**kwargs)

@@ -82,6 +82,12 @@ def preprocess_reasoning_advantages_inputs(rewards, loss_mask, values=None, logp
         kwargs.update({"rewards": expanded})
     elif kwargs["adv_type"] == "grpo":
         kwargs.update({"rewards": rewards.reshape(-1, kwargs["group_size"]).contiguous()})
+    elif kwargs["adv_type"] == "grpo_dynamic":
+        kwargs.update({"rewards": rewards.reshape(-1, kwargs["num_sequence"]).transpose(0, 1).contiguous()})
+    elif kwargs["adv_type"] == "reinpp":
+        kwargs.update({"rewards": rewards.unsqueeze(0)})
+    elif kwargs["adv_type"] == "raw":
+        kwargs.update({"rewards": rewards})
     else:
         assert False, f"Unsupported adv_type {kwargs['adv_type']}"
     if values is not None:
@@ -90,9 +96,9 @@ def preprocess_reasoning_advantages_inputs(rewards, loss_mask, values=None, logp
         values = torch.cat([values, torch.zeros((1, values.shape[-1]), dtype=values.dtype, device=dev)], dim=0)
         kwargs.update({"values": values})
     if logprob is not None:
-        kwargs.update({"logprob": logprob.transpose(0, 1)})
+        kwargs.update({"logprob": L.to_device(logprob, dev, torch.float32).transpose(0, 1)})
     if ref_logprob is not None:
-        kwargs.update({"ref_logprob": ref_logprob.transpose(0, 1)})
+        kwargs.update({"ref_logprob": L.to_device(ref_logprob, dev, torch.float32).transpose(0, 1)})
     dones = torch.zeros(seq_len + 1, bsz, dtype=torch.bool, device=dev)
     dones[-1] = True
     kwargs.update({"dones": dones, "loss_mask": loss_mask})

@@ -62,9 +62,14 @@ __global__ void adamw_prepare_kernel(const double* __restrict__ grad_sq, double*
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                    Groups grp, double beta1, double beta2, double eps, double wd,
-                                                    float grad_scale, const double* __restrict__ state) {
+                                                    Groups grp, const double* __restrict__ lr_dev, double beta1,
+                                                    double beta2, double eps, double wd, float grad_scale,
+                                                    const double* __restrict__ state) {
   if (state[3] != 0.0) return;  // non-finite grad norm: skip the whole step
+  if (lr_dev != nullptr) {      // learning rates live in device memory (LR schedules under CUDA-graph replay)
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) grp.lr[k] = k < grp.n ? lr_dev[k] : 0.0;
+  }
   const double step = state[0];
   const float gmul = (float)state[2] * grad_scale;  // clip coefficient x (1/world_size etc.)
   // scalar factors are formed in double (as Python floats in torch.optim) and rounded once
@@ -72,11 +77,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
   const float one_m_b1 = (float)(1.0 - beta1), b2 = (float)beta2, one_m_b2 = (float)(1.0 - beta2);
   const float eps_f = (float)eps;
+  // lr < 0 marks a FROZEN group: parameters, moments untouched (torch.optim.AdamW skips parameters that are not in a
+  // param group / have grad None: the actor during critic warm-up, fsdp_model_manager.py:523-531; a value head that
+  // received no gradient).  Encoded as step_size = NaN.
   float decay[kMaxGroups], step_size[kMaxGroups];
 #pragma unroll
   for (int k = 0; k < kMaxGroups; ++k) {
     decay[k] = (float)(1.0 - grp.lr[k] * wd);
-    step_size[k] = (float)(grp.lr[k] / bc1);
+    step_size[k] = grp.lr[k] < 0.0 ? __int_as_float(0x7fc00000) : (float)(grp.lr[k] / bc1);
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -87,6 +95,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
         dk = decay[k];
         sk = step_size[k];
       }
+    if (sk != sk) continue;  // frozen group
     const float gi = __fmul_rn(g[i], gmul);
     float pi = p[i];
     pi = __fmul_rn(pi, dk);
@@ -117,11 +126,13 @@ extern "C" int rb200_grad_sqnorm(const float* grads, int64_t n, double* out_sq, 
   RB_RETURN_LAUNCH();
 }
 
-extern "C" int rb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                const int64_t* group_end_host, const double* group_lr_host, int n_groups, double beta1,
-                                double beta2, double eps, double weight_decay, float max_grad_norm, float grad_scale,
-                                const double* grad_sq, double* state, rb200_stream_t stream) {
-  if (!params || !grads || !exp_avg || !exp_avg_sq || !group_end_host || !group_lr_host || !grad_sq || !state)
+static int adamw_step_impl(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* group_end_host, const double* group_lr_host, const double* group_lr_dev,
+                           int n_groups, double beta1, double beta2, double eps, double weight_decay,
+                           float max_grad_norm, float grad_scale, const double* grad_sq, double* state,
+                           rb200_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !group_end_host || (!group_lr_host && !group_lr_dev) || !grad_sq ||
+      !state)
     return RB200_E_NULL;
   if (n <= 0 || n_groups <= 0 || n_groups > kMaxGroups) return RB200_E_SHAPE;
   Groups grp;
@@ -132,7 +143,7 @@ extern "C" int rb200_adamw_step(float* params, const float* grads, float* exp_av
       if (group_end_host[k] < prev || group_end_host[k] > n) return RB200_E_SHAPE;
       prev = group_end_host[k];
       grp.end[k] = group_end_host[k];
-      grp.lr[k] = group_lr_host[k];
+      grp.lr[k] = group_lr_host ? group_lr_host[k] : 0.0;
     } else {
       grp.end[k] = n;
       grp.lr[k] = 0.0;
@@ -144,7 +155,24 @@ extern "C" int rb200_adamw_step(float* params, const float* grads, float* exp_av
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grp, beta1, beta2, eps,
+  adamw_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grp, group_lr_dev, beta1, beta2, eps,
                                             weight_decay, grad_scale, state); rb::count_launch();
   RB_RETURN_LAUNCH();
+}
+
+extern "C" int rb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const int64_t* group_end_host, const double* group_lr_host, int n_groups, double beta1,
+                                double beta2, double eps, double weight_decay, float max_grad_norm, float grad_scale,
+                                const double* grad_sq, double* state, rb200_stream_t stream) {
+  return adamw_step_impl(params, grads, exp_avg, exp_avg_sq, n, group_end_host, group_lr_host, nullptr, n_groups, beta1,
+                         beta2, eps, weight_decay, max_grad_norm, grad_scale, grad_sq, state, stream);
+}
+
+extern "C" int rb200_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    const int64_t* group_end_host, const double* group_lr_dev, int n_groups,
+                                    double beta1, double beta2, double eps, double weight_decay, float max_grad_norm,
+                                    float grad_scale, const double* grad_sq, double* state, rb200_stream_t stream) {
+  if (!group_lr_dev) return RB200_E_NULL;
+  return adamw_step_impl(params, grads, exp_avg, exp_avg_sq, n, group_end_host, nullptr, group_lr_dev, n_groups, beta1,
+                         beta2, eps, weight_decay, max_grad_norm, grad_scale, grad_sq, state, stream);
 }

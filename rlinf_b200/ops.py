@@ -97,8 +97,11 @@ def ppo_loss(*, logprobs, old_logprobs, advantages, C_chunks, A_dim, logprob_typ
              prev_values=None, loss_mask=None, loss_mask_sum=None, mask_sum_row_mod=0, idx=None, entropy=None,
              adv_stats=None, adv_norm_eps=1e-5, clip_ratio_low=0.2, clip_ratio_high=0.2, clip_ratio_c=None,
              clip_log_ratio_min=None, clip_log_ratio_max=None, value_clip=0.0, huber_delta=0.0,
-             max_episode_steps=None, critic_warmup=False, entropy_bonus=0.0, loss_scale=1.0, want_grads=True):
-    """One fused launch group. Returns (loss[1], metrics[24], d_logprobs|None, d_values|None, d_entropy|None)."""
+             max_episode_steps=None, critic_warmup=False, entropy_bonus=0.0, loss_scale=1.0, want_grads=True,
+             _decoupled=None):
+    """One fused launch group. Returns (loss[1], metrics[24], d_logprobs|None, d_values|None, d_entropy|None).
+    `_decoupled` (internal): dict(proximal_logprobs, versions, current_version, behave_weight_threshold) selects
+    rb200_decoupled_ppo_loss (metrics in the RB200_DM_* layout)."""
     lib = L.load()
     dev = logprobs.device
     bsz = logprobs.shape[0]
@@ -144,7 +147,7 @@ def ppo_loss(*, logprobs, old_logprobs, advantages, C_chunks, A_dim, logprob_typ
     a.critic_warmup = int(bool(critic_warmup))
     a.entropy_bonus = float(entropy_bonus)
     a.loss_scale = float(loss_scale)
-    ws = torch.empty(32, dtype=torch.float64, device=dev)
+    ws = _loss_workspace(dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     metrics = torch.empty(L.NUM_METRICS, dtype=torch.float32, device=dev)
     d_lp = torch.empty_like(lp) if want_grads else None
@@ -152,8 +155,50 @@ def ppo_loss(*, logprobs, old_logprobs, advantages, C_chunks, A_dim, logprob_typ
     d_e = torch.empty_like(keep[0]) if (want_grads and entropy is not None) else None
     a.workspace, a.loss, a.metrics = L.ptr(ws), L.ptr(loss), L.ptr(metrics)
     a.d_logprobs, a.d_values, a.d_entropy = L.ptr(d_lp), L.ptr(d_v), L.ptr(d_e)
+    if _decoupled is not None:
+        d = L.DppoArgs()
+        d.base = a
+        d.proximal_logprobs = P(_decoupled.get("proximal_logprobs"), torch.float32)
+        d.versions = P(_decoupled.get("versions"), torch.float32)
+        cv, thr = _decoupled.get("current_version"), _decoupled.get("behave_weight_threshold")
+        d.has_current_version, d.current_version = int(cv is not None), float(cv or 0.0)
+        d.has_behave_weight_threshold, d.behave_weight_threshold = int(thr is not None), float(thr or 0.0)
+        L.check(lib.rb200_decoupled_ppo_loss(C.byref(d), L.stream_ptr()), "decoupled_ppo_loss")
+        return loss, metrics, d_lp, d_v, d_e
     L.check(lib.rb200_ppo_loss(C.byref(a), L.stream_ptr()), "ppo_loss")
     return loss, metrics, d_lp, d_v, d_e
+
+
+def opd_loss(*, logprobs, advantages, loss_mask, loss_mask_sum, max_episode_steps=None, loss_scale=1.0, want_grads=True):
+    """compute_opd_actor_loss (losses.py:427-505). logprobs/advantages [n_units, tokens]; mask/mask_sum [n_units]."""
+    lib = L.load()
+    lp = logprobs.contiguous()
+    dev = lp.device
+    n_units, g = lp.shape
+    adv = L.to_device(advantages, dev, torch.float32).reshape(n_units, g)
+    m = L.as_u8(L.to_device(loss_mask, dev)).reshape(n_units).contiguous()
+    ms = L.to_device(loss_mask_sum, dev, torch.int64).reshape(n_units).contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    metrics = torch.empty(L.NUM_METRICS, dtype=torch.float32, device=dev)
+    d_lp = torch.empty_like(lp) if want_grads else None
+    L.check(lib.rb200_opd_loss(L.ptr(lp), L.ptr(adv), L.ptr(m), L.ptr(ms), n_units, g, int(max_episode_steps or 0),
+                               float(loss_scale), L.ptr(_loss_workspace(dev)), L.ptr(loss), L.ptr(metrics), L.ptr(d_lp),
+                               L.stream_ptr()), "opd_loss")
+    return loss, metrics, d_lp
+
+
+_WS: dict = {}
+
+
+def _loss_workspace(dev) -> torch.Tensor:
+    """Zero-initialised, self-cleaning reduction workspace of the loss kernels, one per device: the loss kernels of
+    one process are stream-ordered (training loop / one CUDA graph), which is what sharing it requires."""
+    key = dev.index
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.zeros(32, dtype=torch.float64, device=dev)
+        _WS[key] = ws
+    return ws
 
 
 def scale_(x: torch.Tensor, s: float) -> torch.Tensor:
@@ -210,4 +255,106 @@ def masked_stats(x, mask=None, mask_div=1):
     out = torch.empty(4, dtype=torch.float64, device=xs.device)
     L.check(lib.rb200_masked_stats(L.ptr(xs), L.ptr(m.contiguous() if m is not None else None), xs.numel(),
                                    int(mask_div), L.ptr(out), L.stream_ptr()), "masked_stats")
+    return out
+
+
+# ---- remaining advantage estimators, fp64 masked normalisations -----------------------------------
+def masked_moments(x, mask=None) -> torch.Tensor:
+    """{count, sum, sumsq} (float64[3], device) of x over mask - masked_stats (rlinf/utils/distributed.py:942-954)."""
+    lib = L.load()
+    xs = L.to_device(x, dtype=torch.float32).contiguous()
+    m = L.as_u8(L.to_device(mask, xs.device))
+    if m is not None:
+        if m.shape != xs.shape:
+            raise AssertionError((tuple(m.shape), tuple(xs.shape)))
+        m = m.contiguous()
+    out = torch.empty(3, dtype=torch.float64, device=xs.device)
+    L.check(lib.rb200_masked_moments(L.ptr(xs), L.ptr(m), xs.numel(), L.ptr(out), L.stream_ptr()), "masked_moments")
+    return out
+
+
+def masked_normalize(x, stats3, mask=None, mode=0, eps=1e-5, unbiased=False) -> torch.Tensor:
+    """Apply half of the fp64 normalisations (mode 0 masked_normalization, 1 normalize_from_stats, 2 whitening)."""
+    lib = L.load()
+    xs = L.to_device(x, dtype=torch.float32).contiguous()
+    m = L.as_u8(L.to_device(mask, xs.device))
+    m = m.contiguous() if m is not None else None
+    out = torch.empty_like(xs)
+    st = L.to_device(stats3, xs.device, torch.float64)
+    L.check(lib.rb200_masked_normalize(L.ptr(xs), L.ptr(m), L.ptr(out), xs.numel(), L.ptr(st), int(mode), float(eps),
+                                       int(bool(unbiased)), L.stream_ptr()), "masked_normalize")
+    return out
+
+
+def raw_advantages(scores, loss_mask, want_stats=False):
+    lib = L.load()
+    s = L.to_device(scores, dtype=torch.float32).reshape(-1).contiguous()
+    m = L.as_u8(L.to_device(loss_mask, s.device)).contiguous()
+    Ln, B = m.shape
+    if s.numel() != B:
+        raise RuntimeError(f"{s.numel()} scores for a loss_mask of {tuple(m.shape)}")
+    adv = torch.empty((Ln, B), dtype=torch.float32, device=s.device)
+    stats = torch.empty(3, dtype=torch.float64, device=s.device) if want_stats else None
+    L.check(lib.rb200_raw_advantages(L.ptr(s), L.ptr(m), L.ptr(adv), Ln, B, L.ptr(stats), L.stream_ptr()), "raw_advantages")
+    return adv, stats
+
+
+def reinpp_returns(rewards, loss_mask, kl_beta=0.0, logprob=None, ref_logprob=None, kl_kind="k1"):
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32).reshape(-1).contiguous()
+    m = L.as_u8(L.to_device(loss_mask, r.device)).contiguous()
+    Ln, B = m.shape
+    if r.numel() != B:
+        raise RuntimeError(f"{r.numel()} rewards for a loss_mask of {tuple(m.shape)}")
+    lp = rlp = None
+    if kl_beta > 0:
+        if kl_kind not in _KL_MODES:
+            raise NotImplementedError(kl_kind)
+        lp = L.to_device(logprob, r.device, torch.float32).contiguous()
+        rlp = L.to_device(ref_logprob, r.device, torch.float32).contiguous()
+        if lp.shape != m.shape or rlp.shape != m.shape:
+            raise RuntimeError("logprob / ref_logprob must be [L, B] like loss_mask")
+    ret = torch.empty((Ln, B), dtype=torch.float32, device=r.device)
+    stats = torch.empty(3, dtype=torch.float64, device=r.device)
+    L.check(lib.rb200_reinpp_returns(L.ptr(r), L.ptr(m), L.ptr(lp), L.ptr(rlp), L.ptr(ret), Ln, B, float(kl_beta),
+                                     _KL_MODES.get(kl_kind, 0), L.ptr(stats), L.stream_ptr()), "reinpp_returns")
+    return ret, stats
+
+
+def grpo_video_advantages(rewards, loss_mask, group_size, mode):
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32).contiguous()
+    S, B = r.shape
+    mf = m8 = None
+    if loss_mask is not None:
+        lm = L.to_device(loss_mask, r.device)
+        if lm.dtype in (torch.bool, torch.uint8):
+            m8 = L.as_u8(lm).contiguous()
+        else:
+            mf = lm.to(torch.float32).contiguous()
+    adv = torch.empty_like(r)
+    L.check(lib.rb200_grpo_video_advantages(L.ptr(r), L.ptr(mf), L.ptr(m8), L.ptr(adv), S, B, int(group_size),
+                                            {"frame": 0, "video": 1}[mode], 1e-6, L.stream_ptr()), "grpo_video")
+    return adv
+
+
+def grpo_dynamic_turn_advantages(rewards, idx_to_traj, group_size, mode):
+    lib = L.load()
+    r = L.to_device(rewards, dtype=torch.float32).reshape(-1).contiguous()
+    idx = torch.as_tensor(idx_to_traj, dtype=torch.int32).to(r.device)
+    n = idx.numel()
+    n_traj = int(max(idx_to_traj)) + 1
+    out = torch.zeros(n, dtype=torch.float32, device=r.device)
+    L.check(lib.rb200_grpo_dynamic_turn_advantages(L.ptr(r), L.ptr(idx), L.ptr(out), n, n_traj, int(group_size),
+                                                   {"trajectory": 0, "turn": 1}[mode], 1e-6, L.stream_ptr()),
+            "grpo_dynamic")
+    return out
+
+
+def sub(a, b) -> torch.Tensor:
+    lib = L.load()
+    x = L.to_device(a, dtype=torch.float32).contiguous()
+    y = L.to_device(b, x.device, torch.float32).contiguous()
+    out = torch.empty_like(x)
+    L.check(lib.rb200_sub(L.ptr(x), L.ptr(y), L.ptr(out), x.numel(), L.stream_ptr()), "sub")
     return out

@@ -233,31 +233,60 @@ class FlatAdamW:
         segs = policy.lr_group_ends()
         self._ends = (C.c_int64 * len(segs))(*[e for _, e in segs])
         self._kinds = [k for k, _ in segs]
-        self.lr_scale = 1.0
+        self.lr_scale = 1.0          # LambdaLR multiplier (rlinf_b200/lr_scheduler.py), set once per run_training
+        self.frozen: set = set()     # group kinds ("actor" / "critic") the next steps leave untouched
+        # per-segment learning rates in device memory: a captured optimiser step follows LR schedules / warm-up
+        self._lr_dev = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._lr_key = None
 
     def zero_grad(self):
         self.policy.flat_grads.zero_()
+
+    def _segment_lrs(self):
+        return [-1.0 if k in self.frozen else (self.value_lr if k == "critic" else self.lr) * self.lr_scale
+                for k in self._kinds]
+
+    def sync_lr_table(self):
+        """Upload the per-segment lr table if it changed (call OUTSIDE graph capture; replays read the device copy)."""
+        lrs = self._segment_lrs()
+        key = tuple(lrs)
+        if key != self._lr_key:
+            host = torch.zeros(8, dtype=torch.float64)
+            host[: len(lrs)] = torch.tensor(lrs, dtype=torch.float64)
+            self._lr_dev.copy_(host)  # stream-ordered H2D of 64 bytes, only when the table changes
+            self._lr_key = key
 
     def step(self, grad_scale: float = 1.0):
         lib = L.load()
         p = self.policy
         n = p.flat_params.numel()
         st = L.stream_ptr()
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr_table()
         L.check(lib.rb200_grad_sqnorm(L.ptr(p.flat_grads), n, L.ptr(self.grad_sq), st), "grad_sqnorm")
-        lrs = (C.c_double * len(self._kinds))(*[
-            (self.value_lr if k == "critic" else self.lr) * self.lr_scale for k in self._kinds])
-        L.check(lib.rb200_adamw_step(L.ptr(p.flat_params), L.ptr(p.flat_grads), L.ptr(self.exp_avg),
-                                     L.ptr(self.exp_avg_sq), n, self._ends, lrs, len(self._kinds), self.betas[0],
-                                     self.betas[1], self.eps, self.weight_decay, self.clip_grad, float(grad_scale),
-                                     L.ptr(self.grad_sq), L.ptr(self.state), st), "adamw_step")
+        L.check(lib.rb200_adamw_step_dev(L.ptr(p.flat_params), L.ptr(p.flat_grads), L.ptr(self.exp_avg),
+                                         L.ptr(self.exp_avg_sq), n, self._ends, L.ptr(self._lr_dev), len(self._kinds),
+                                         self.betas[0], self.betas[1], self.eps, self.weight_decay, self.clip_grad,
+                                         float(grad_scale), L.ptr(self.grad_sq), L.ptr(self.state), st), "adamw_step")
         p.mark_params_changed()
+
+    def reset_state(self):
+        """Fresh moments and step count: the reference REBUILDS its optimiser when critic warm-up ends
+        (fsdp_model_manager.py:452-459)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.state[0].zero_()
 
     def last_grad_norm(self) -> torch.Tensor:
         """0-dim device tensor (read it on the host once per run_training, not per step)."""
         return self.state[1]
 
     def lr_list(self):
-        lrs = [self.lr * self.lr_scale]
-        if "critic" in self._kinds:
+        """[group["lr"] for group in optimizer.param_groups]: actor group first, then the value-head group; frozen
+        groups are not part of the reference's (warm-up) optimiser."""
+        lrs = []
+        if "actor" not in self.frozen:
+            lrs.append(self.lr * self.lr_scale)
+        if "critic" in self._kinds and "critic" not in self.frozen:
             lrs.append(self.value_lr * self.lr_scale)
         return lrs

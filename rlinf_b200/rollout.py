@@ -18,11 +18,81 @@ captured once in a CUDA graph (rollout.enable_cuda_graph) and replayed - any env
 """
 from __future__ import annotations
 
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
 import torch
 
-import ctypes as C
-
 from . import _lib as L
+
+
+@dataclass
+class Trajectory:
+    """Field-for-field counterpart of rlinf.data.schema.embodied_types.Trajectory (:380-398) for the tensors this path
+    produces.  Instances handed out by RolloutBuffer are VIEWS of the device buffer (no stack / cat / .cpu())."""
+
+    max_episode_length: int = 0
+    model_weights_id: str = ""
+    actions: Optional[torch.Tensor] = None
+    intervene_flags: Optional[torch.Tensor] = None
+    rewards: Optional[torch.Tensor] = None
+    terminations: Optional[torch.Tensor] = None
+    truncations: Optional[torch.Tensor] = None
+    dones: Optional[torch.Tensor] = None
+    prev_logprobs: Optional[torch.Tensor] = None
+    prev_values: Optional[torch.Tensor] = None
+    versions: Optional[torch.Tensor] = None
+    forward_inputs: dict = field(default_factory=dict)
+    curr_obs: dict = field(default_factory=dict)
+    next_obs: dict = field(default_factory=dict)
+
+
+_TRAJ_TENSOR_FIELDS = ("actions", "intervene_flags", "rewards", "terminations", "truncations", "dones", "prev_logprobs",
+                       "prev_values", "versions")
+
+
+def _adjacent_views(parts) -> Optional[torch.Tensor]:
+    """If `parts` are consecutive column slices [:, lo:hi] of ONE tensor, return that parent slice (zero copy)."""
+    first = parts[0]
+    if any(p.dim() < 2 or p.stride() != first.stride() or p.shape[0] != first.shape[0] or p.dtype != first.dtype or
+           p.shape[2:] != first.shape[2:] for p in parts):
+        return None
+    step = first.stride(1) * first.element_size()
+    ptr, cols = first.data_ptr(), 0
+    for p in parts:
+        if p.data_ptr() != ptr + cols * step or p.untyped_storage().data_ptr() != first.untyped_storage().data_ptr():
+            return None
+        cols += p.shape[1]
+    return first.as_strided((first.shape[0], cols, *first.shape[2:]), first.stride(), first.storage_offset())
+
+
+def convert_trajectories_to_batch(trajectories: list) -> dict:
+    """[T, B, ...] batch dict from a list of trajectories (embodied_types.py:500-559: torch.cat over dim 1).  Parts that
+    are adjacent views of the rollout buffer are re-joined without copying."""
+    if not trajectories:
+        return {}
+
+    def join(parts):
+        parts = [p for p in parts if p is not None]
+        if not parts:
+            return None
+        if len(parts) == 1:
+            return parts[0]
+        joined = _adjacent_views(parts)
+        return joined if joined is not None else torch.cat(parts, dim=1)
+
+    batch: dict = {}
+    for group in ("curr_obs", "next_obs", "forward_inputs"):
+        if getattr(trajectories[0], group):
+            keys = []
+            for t in trajectories:
+                keys += [k for k in getattr(t, group) if k not in keys]
+            batch[group] = {k: join([getattr(t, group).get(k) for t in trajectories]) for k in keys}
+    for name in _TRAJ_TENSOR_FIELDS:
+        if isinstance(getattr(trajectories[0], name), torch.Tensor):
+            batch[name] = join([getattr(t, name) for t in trajectories])
+    return batch
 
 
 class RolloutBuffer:
@@ -52,6 +122,36 @@ class RolloutBuffer:
             "prev_logprobs": self.prev_logprobs,
             "forward_inputs": {"states": self.states[: self.T], "action": self.actions},
         }
+
+    def to_trajectory(self, max_episode_length: int = 0, version: Optional[int] = None) -> Trajectory:
+        """EmbodiedTrajectoryBuilder.to_trajectory (embodied_trajectory_builder.py:176-230) as views of the buffer."""
+        b = self.as_batch()
+        traj = Trajectory(max_episode_length=max_episode_length, actions=self.actions, rewards=b["rewards"],
+                          terminations=b["terminations"], truncations=b["truncations"], dones=b["dones"],
+                          prev_logprobs=b["prev_logprobs"], prev_values=b["prev_values"],
+                          forward_inputs=dict(b["forward_inputs"]))
+        if version is not None:
+            traj.model_weights_id = str(version)
+        return traj
+
+    def to_splited_trajectories(self, split_size: int, max_episode_length: int = 0) -> list:
+        """to_splited_trajectories (embodied_trajectory_builder.py:232-283): torch.chunk over the env dimension - here
+        `split_size` column views of the same buffer (the reference makes each chunk contiguous, i.e. copies)."""
+        full = self.to_trajectory(max_episode_length)
+        if self.B % split_size != 0:
+            raise ValueError(f"{self.B} envs cannot be split into {split_size} equal trajectories")
+        w = self.B // split_size
+        parts = []
+        for i in range(split_size):
+            sl = slice(i * w, (i + 1) * w)
+            p = Trajectory(max_episode_length=full.max_episode_length, model_weights_id=full.model_weights_id)
+            for name in _TRAJ_TENSOR_FIELDS:
+                v = getattr(full, name)
+                if v is not None:
+                    setattr(p, name, v[:, sl])
+            p.forward_inputs = {k: v[:, sl] for k, v in full.forward_inputs.items()}
+            parts.append(p)
+        return parts
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (
@@ -158,7 +258,9 @@ class RolloutWorker:
     def generate(self):
         """One rollout epoch of T steps into the buffer (all on the current stream, no host sync)."""
         buf = self.buf
-        if not self.started:
+        if not self.started or not self.auto_reset:
+            # bootstrap_step (env_worker.py:908-935): with auto_reset off the envs are reset at EVERY rollout epoch
+            # (elapsed back to 0, fresh initial states); with auto_reset on only once, at the very beginning
             obs, _ = self.env.reset()
             buf.states[0].copy_(obs["states"])
             self.started = True
