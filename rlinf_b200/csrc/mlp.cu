@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadFwdArgs p) {
           z = p.noise[row * p.act + lane];
         } else {
           curandStatePhilox4_32_10_t st;
-          curand_init(p.seed, (unsigned long long)(row * p.act + lane), p.offset + (p.counter ? p.counter[0] : 0ull), &st);
+          // the Philox offset counts 32-bit outputs and curand_normal consumes two (Box-Muller): stride 4 per env step so
+          // that consecutive steps never share a word (round 1 used stride 1: the angle word of step t was the radius
+          // word of step t+1)
+          curand_init(p.seed, (unsigned long long)(row * p.act + lane), p.offset + 4ull * (p.counter ? p.counter[0] : 0ull), &st);
           z = curand_normal(&st);
         }
         x = my_mean + sd * z;

@@ -30,6 +30,11 @@ class EmbodiedRunner:
         self.env_start, self.B = shard_envs(et.total_num_envs, self.world_size, self.rank,
                                             cfg.algorithm.get("group_size", 1))  # envs owned by this rank
         self.T = et.max_steps_per_rollout_epoch
+        if m.get("num_action_chunks", 1) != 1:
+            # the device rollout (buffer rows, env kernels, fused kernel) is written for one action per env step; the
+            # advantage / loss kernels handle num_action_chunks > 1 (tested), the synthetic rollout does not
+            raise NotImplementedError("EmbodiedRunner's device rollout implements num_action_chunks == 1 (MLP policy "
+                                      "configs); feed chunked batches to EmbodiedActor directly")
         self.actor = EmbodiedActor(cfg, rank=self.rank, world_size=self.world_size, process_group=process_group)
         pol = self.actor.model
         self.env = SyntheticVectorEnv(self.B, m.obs_dim, m.action_dim * m.get("num_action_chunks", 1),

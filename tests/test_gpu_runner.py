@@ -148,12 +148,10 @@ def test_fused_rollout_matches_per_kernel_path(B):
     assert bool(bufs[0][2]["dones"].any())
 
 
-@pytest.mark.skipif(os.environ.get("RB200_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernel variants (rb200_debug_set_flags): RB200_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("B", [300, 1000, 2000, 4096])
-def test_experimental_fused_rollout_prefetch_variants_bit_identical(B):
-    """Deeper weight prefetch (debug flag bit 1) keeps the k-ascending fmaf order: buffers must be bit-identical
-    to the validated fused kernels."""
+def test_fused_rollout_prefetch_variants_bit_identical(B):
+    """The default kernels keep 4 k-steps of weight rows in flight; debug flag bit 1 selects the round-1 one-step
+    prefetch. Same k-ascending fmaf order: the buffers must be bit-identical."""
     from rlinf_b200 import _lib as L
     from rlinf_b200.config import synthetic_ppo_config
     from rlinf_b200.runner import EmbodiedRunner
