@@ -130,13 +130,46 @@ def effective_cores() -> int:
     return max(1, n)
 
 
-def cpu_iteration_rate(a, n_envs, steps, warmup):
+_BEST_THREADS = None
+
+
+def best_thread_count(a) -> int:
+    """The oracle's eager-PyTorch ops on [4096]-element rows do not scale with threads (round 1: 20.2 k env-steps/s with
+    16 threads on a 16-core box, 12.3 k with 96 threads on a 96-core box): time one small iteration per candidate thread
+    count and keep the fastest, so the baseline is the best the host can do."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
     import torch
 
     from oracle.runner_oracle import RunnerOracle
     from rlinf_b200.config import synthetic_ppo_config
 
     cores = effective_cores()
+    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
+    best, best_t = cores, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        cfg = synthetic_ppo_config(B=512, T=64, obs_dim=a.obs, action_dim=a.act, update_epoch=1, num_minibatches=2)
+        r = RunnerOracle(cfg)
+        r.run_iteration()
+        t0 = time.perf_counter()
+        r.run_iteration()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    log(f"cpu thread calibration: {cands} -> {best} threads")
+    _BEST_THREADS = best
+    return best
+
+
+def cpu_iteration_rate(a, n_envs, steps, warmup):
+    import torch
+
+    from oracle.runner_oracle import RunnerOracle
+    from rlinf_b200.config import synthetic_ppo_config
+
+    cores = best_thread_count(a)
     torch.set_num_threads(cores)
     cfg = synthetic_ppo_config(B=n_envs, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,
                                num_minibatches=a.minibatches)
@@ -154,24 +187,109 @@ def cpu_iteration_rate(a, n_envs, steps, warmup):
     return n_envs * a.T / mean, mean, cores, phases
 
 
+def reference_functions_check(a):
+    """When /root/reference exists (build container only - never on the GPU box): time the reference's OWN
+    calculate_adv_and_returns (GAE) and policy_loss (actor_critic, forward + backward) through tests/golden/ref_loader.py
+    beside the oracle port on the same inputs, to show port ~= reference. Returns None when the reference is absent."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import ref_loader
+
+        if not ref_loader.reference_available():
+            return None
+        ref = ref_loader.load_reference()
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+    import torch
+
+    from oracle import rl_oracle as O
+
+    T, B, A = a.T, min(a.B, 512), a.act
+    g = torch.Generator().manual_seed(0)
+    rewards, values = torch.randn(T, B, 1, generator=g), torch.randn(T + 1, B, 1, generator=g)
+    dones = torch.rand(T + 1, B, 1, generator=g) < 0.01
+    dones[0] = False
+    n = T * B
+    old = -1 + 0.3 * torch.randn(n, A, generator=g)
+    adv, ret, pv = (torch.randn(n, 1, generator=g) for _ in range(3))
+
+    def timed(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    def ref_adv():
+        return ref.registry.calculate_adv_and_returns(task_type="embodied", adv_type="gae", rewards=rewards, dones=dones,
+                                                      values=values, gamma=0.99, gae_lambda=0.95, group_size=8,
+                                                      reward_type="action_level", num_action_chunks=1, loss_mask=None,
+                                                      loss_mask_sum=None)
+
+    def port_adv():
+        return O.adv_and_returns_embodied("gae", rewards, dones, values, gamma=0.99, gae_lambda=0.95)
+
+    def loss_inputs():
+        new = (old + 0.05 * torch.randn(n, A, generator=g)).requires_grad_(True)
+        val = (pv + 0.1 * torch.randn(n, 1, generator=g)).requires_grad_(True)
+        return new, val
+
+    def ref_loss():
+        new, val = loss_inputs()
+        loss, _ = ref.registry.policy_loss(task_type="embodied", loss_type="actor_critic", logprob_type="action_level",
+                                           reward_type="action_level", single_action_dim=A, logprobs=new, values=val,
+                                           old_logprobs=old, advantages=adv, returns=ret, prev_values=pv,
+                                           clip_ratio_high=0.2, clip_ratio_low=0.2, value_clip=0.2, huber_delta=10.0,
+                                           loss_mask=None, loss_mask_sum=None, max_episode_steps=128, critic_warmup=False)
+        loss.backward()
+
+    def port_loss():
+        new, val = loss_inputs()
+        loss, _ = O.policy_loss_embodied("actor_critic", new, old, adv, "action_level", A, values=val, prev_values=pv,
+                                         returns=ret, clip_ratio_low=0.2, clip_ratio_high=0.2, value_clip=0.2,
+                                         huber_delta=10.0)
+        loss.backward()
+
+    return {"shape": f"T={T} B={B} A={A}", "gae_s": {"reference": timed(ref_adv), "port": timed(port_adv)},
+            "loss_fwd_bwd_s": {"reference": timed(ref_loss), "port": timed(port_loss)}}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_envs = min(a.cpu_envs or 256, a.B)
-    value, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, a.steps, a.warmup)
-    sample = (f"{n_envs} of {a.B} envs x T={a.T} per step (same update_epoch/mini-batch structure); "
-              f"oracle port of the reference CPU path (torch {cores} threads = usable host cores); the reference's own Ray runner "
-              f"cannot be launched offline")
+    # 1. a small sample (warm caches, estimate the rate), 2. as many FULL-size iterations as fit the time budget
+    #    (4096 envs x 512 steps is ~2 min per iteration on 16 cores): `same config` as the GPU arm whenever >= 1 fits
+    small = min(a.cpu_envs or 256, a.B)
+    v_small, mean_small, cores, phases = cpu_iteration_rate(a, small, 1, max(1, min(a.warmup, 1)))
+    budget_s = float(os.environ.get("RB200_REF_BUDGET_S", "240"))
+    est_full = a.B * a.T / v_small
+    n_full = int(min(a.steps, budget_s // est_full)) if not a.cpu_envs else 0
+    if n_full >= 1:
+        value, mean_s, cores, phases = cpu_iteration_rate(a, a.B, n_full, 0)
+        sample = (f"FULL workload: {n_full} iteration(s) of {a.B} envs x T={a.T} (of --steps {a.steps}: bounded by a "
+                  f"{budget_s:.0f} s budget), after a {small}-env warm-up iteration; oracle port of the reference CPU path, "
+                  f"torch {cores} threads (fastest of a calibration over thread counts; usable host cores: "
+                  f"{effective_cores()}); the reference's own Ray runner cannot be launched offline")
+        n_envs = a.B
+    else:
+        n_envs = small
+        value, mean_s, cores, phases = cpu_iteration_rate(a, n_envs, a.steps, a.warmup)
+        sample = (f"{n_envs} of {a.B} envs x T={a.T} per step (same update_epoch/mini-batch structure); "
+                  f"oracle port of the reference CPU path (torch {cores} threads, fastest of a calibration; usable host "
+                  f"cores: {effective_cores()}); the reference's own Ray runner cannot be launched offline")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "B": a.B, "T": a.T, "obs_dim": a.obs, "act_dim": a.act},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "phases_s": phases},
+                         "phases_s": phases, "envs_timed": n_envs},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    chk = reference_functions_check(a)
+    if chk is not None:
+        line["cpu_baseline"]["port_vs_reference_functions"] = chk
     print(json.dumps(line), flush=True)
 
 

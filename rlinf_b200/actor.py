@@ -388,5 +388,7 @@ class EmbodiedActor:
         if rollout_params is not None and rollout_params.data_ptr() != self.model.flat_params.data_ptr():
             rollout_params.copy_(self.model.flat_params)
         if self.cfg.runner.get("broadcast_params", True):
-            D.broadcast_params(self.model.flat_params, self._world_size, src, self.pg)
+            from .weight_sync import broadcast_flat
+
+            self.rollout_version = broadcast_flat(self.model, self.version, src, self.pg)
         self.model.mark_params_changed()

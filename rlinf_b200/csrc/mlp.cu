@@ -154,6 +154,8 @@ struct HeadBwdArgs {
   float* g_vw3;             // [vdim,256] +=
   float* g_b2;              // [256] += column sums of dz3 (bias gradient of backbone layer 3)
   float* g_vb2;             // [256] += column sums of dy3 (value layer 3)
+  float* amax_dz3;          // [1] atomicMax |dz3| (operand scaling of the fp16-split gradient GEMMs), or null
+  float* amax_dy3;          // [1] atomicMax |dy3|, or null
   int64_t n;
   int act, vdim;
 };
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float cb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float mz = 0.f, my = 0.f;  // running max |dz3|, |dy3|
   float rm[REG ? 8 : 1][8], rv[REG ? 2 : 1][8];
 #pragma unroll
   for (int a = 0; a < (REG ? 8 : 1); ++a)
@@ -275,6 +278,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
     *reinterpret_cast<float4*>(p.dz3 + row * kH + 128 + lane * 4) = o1;
     cb[0] += o0.x; cb[1] += o0.y; cb[2] += o0.z; cb[3] += o0.w;
     cb[4] += o1.x; cb[5] += o1.y; cb[6] += o1.z; cb[7] += o1.w;
+    mz = fmaxf(mz, fmaxf(fmaxf(fmaxf(fabsf(o0.x), fabsf(o0.y)), fmaxf(fabsf(o0.z), fabsf(o0.w))),
+                         fmaxf(fmaxf(fabsf(o1.x), fabsf(o1.y)), fmaxf(fabsf(o1.z), fabsf(o1.w)))));
 
     if (has_v) {
       const float4 g0 = cur.g0, g1 = cur.g1;
@@ -308,6 +313,19 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs p) {
       *reinterpret_cast<float4*>(p.dy3 + row * kH + 128 + lane * 4) = q1;
       cv[0] += q0.x; cv[1] += q0.y; cv[2] += q0.z; cv[3] += q0.w;
       cv[4] += q1.x; cv[5] += q1.y; cv[6] += q1.z; cv[7] += q1.w;
+      my = fmaxf(my, fmaxf(fmaxf(fmaxf(fabsf(q0.x), fabsf(q0.y)), fmaxf(fabsf(q0.z), fabsf(q0.w))),
+                           fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fmaxf(fabsf(q1.z), fabsf(q1.w)))));
+    }
+  }
+  if (p.amax_dz3 != nullptr) {  // non-negative floats order like their bit patterns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+      my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, o));
+    }
+    if (lane == 0) {
+      if (mz > 0.f) atomicMax(reinterpret_cast<unsigned int*>(p.amax_dz3), __float_as_uint(mz));
+      if (has_v && my > 0.f && p.amax_dy3) atomicMax(reinterpret_cast<unsigned int*>(p.amax_dy3), __float_as_uint(my));
     }
   }
   // bias gradients of the two layer-3 pre-activations (lane owns columns lane*4..+3 and 128+lane*4..+3)
@@ -454,6 +472,75 @@ int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, co
   return wgrad(tmpB, X, idx, in_dim, g_w0, g_b0, !tc);
 }
 
+// ---- round 2: fp16-split tensor-core path (tc_gemm_h.cu), both towers per launch -------------------------------------------
+// debug flag bit 3 (value 8) selects the round-1 3xTF32 kernels instead.
+inline bool half_mode() { return (rb::tc::g_debug_flags & 8) == 0; }
+
+struct TowerWH {  // fp16 (hi, lo) copies of w * 2^10, [256 out, in] as stored; typed float* (they live in the wsplit buffer)
+  const float *w0h, *w0l, *w1h, *w1l, *w2h, *w2l;
+};
+
+struct TowerIO {  // one tower of a grouped forward / backward
+  TowerW w;
+  TowerWH wh;
+  float *H1, *H2, *H3;                               // activations (forward: outputs)
+  float *g_w0, *g_b0, *g_w1, *g_b1, *g_w2, *g_b2;    // parameter gradients (backward)
+  const float* dZ3;                                  // backward: gradient wrt the layer-3 pre-activation
+  float *tA, *tB;                                    // backward: dZ2, dZ1 scratch
+  float* amax;                                       // backward: [3] max|dZ3|, max|dZ2|, max|dZ1| (device)
+};
+
+// X -> H1 -> H2 -> H3 for `nt` towers sharing the input X
+int towers_forward_h(const float* X, const int64_t* idx, int64_t n, int in_dim, TowerIO* t, int nt, cudaStream_t st) {
+  int e;
+  const bool l0_tc = idx == nullptr && (in_dim % rb::tc::BK == 0);
+  rb::tch::GemmLaunch g[2];
+  if (l0_tc) {
+    for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{X, t[i].wh.w0h, t[i].wh.w0l, t[i].H1, t[i].w.b0, nullptr, nullptr, nullptr, nullptr};
+    if ((e = rb::tch::launch(g, nt, n, in_dim, rb::tc::EPI_BIAS_TANH, 0, st))) return e;
+  } else {
+    for (int i = 0; i < nt; ++i)
+      if ((e = layer_forward(X, idx, n, in_dim, t[i].w.w0, t[i].w.b0, nullptr, nullptr, t[i].H1, st))) return e;
+  }
+  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H1, t[i].wh.w1h, t[i].wh.w1l, t[i].H2, t[i].w.b1, nullptr, nullptr, nullptr, nullptr};
+  if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_BIAS_TANH, 0, st))) return e;
+  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H2, t[i].wh.w2h, t[i].wh.w2l, t[i].H3, t[i].w.b2, nullptr, nullptr, nullptr, nullptr};
+  return rb::tch::launch(g, nt, n, kH, rb::tc::EPI_BIAS_TANH, 0, st);
+}
+
+// backward through the hidden layers of `nt` towers given their dZ3 (and max|dZ3| in amax[0])
+int towers_backward_h(const float* X, const int64_t* idx, int64_t n, int in_dim, TowerIO* t, int nt, cudaStream_t st) {
+  int e;
+  rb::tch::WgradLaunch w[2];
+  rb::tch::GemmLaunch g[2];
+  // layer 2: dW2 += dZ3^T . H2 ; dZ2 = (dZ3 . W2) * (1 - H2^2)  (+ column sums -> g_b1, max|dZ2| -> amax[1])
+  for (int i = 0; i < nt; ++i) w[i] = rb::tch::WgradLaunch{t[i].dZ3, t[i].H2, t[i].g_w2, t[i].amax};
+  if ((e = rb::tch::wgrad(w, nt, n, kH, st))) return e;
+  for (int i = 0; i < nt; ++i)
+    g[i] = rb::tch::GemmLaunch{t[i].dZ3, t[i].wh.w2h, t[i].wh.w2l, t[i].tA, nullptr, t[i].H2, t[i].g_b1, t[i].amax, t[i].amax + 1};
+  if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_TANHGRAD, 1, st))) return e;
+  // layer 1
+  for (int i = 0; i < nt; ++i) w[i] = rb::tch::WgradLaunch{t[i].tA, t[i].H1, t[i].g_w1, t[i].amax + 1};
+  if ((e = rb::tch::wgrad(w, nt, n, kH, st))) return e;
+  for (int i = 0; i < nt; ++i)
+    g[i] = rb::tch::GemmLaunch{t[i].tA, t[i].wh.w1h, t[i].wh.w1l, t[i].tB, nullptr, t[i].H1, t[i].g_b0, t[i].amax + 1, t[i].amax + 2};
+  if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_TANHGRAD, 1, st))) return e;
+  // layer 0: dW0 += dZ1^T . X
+  if (idx == nullptr && (in_dim % rb::tc::BK == 0) && in_dim <= 256) {
+    for (int i = 0; i < nt; ++i) w[i] = rb::tch::WgradLaunch{t[i].tB, X, t[i].g_w0, t[i].amax + 2};
+    return rb::tch::wgrad(w, nt, n, in_dim, st);
+  }
+  const int64_t rows_per_split = 4096;
+  const int splits = (int)((n + rows_per_split - 1) / rows_per_split);
+  for (int i = 0; i < nt; ++i) {
+    GemmArgs a{};
+    a.A = t[i].tB; a.lda = kH; a.B = X; a.ldb = in_dim; a.b_rows = idx; a.C = t[i].g_w0;
+    a.ldc = in_dim; a.M = kH; a.N = in_dim; a.K = n; a.k_per_split = rows_per_split;
+    if ((e = launch_gemm<A_MCONTIG, B_NCONTIG, EPI_ATOMIC>(a, splits, st))) return e;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int rb200_mlp_layout_init(rb200_mlp_layout* L, int obs_dim, int act_dim, int value_dim, int hidden) {
@@ -525,6 +612,18 @@ TowerWS tower_ws(const rb200_mlp_layout* L, const float* ws, bool value) {
   t.w1th = q + 4 * nn; t.w1tl = q + 5 * nn; t.w2th = q + 6 * nn; t.w2tl = q + 7 * nn;
   return t;
 }
+// fp16-split cache: per tower (value tower first) w0 hi|lo [256*obs halves each], w1 hi|lo, w2 hi|lo [65536 halves each];
+// it needs half the floats of the TF32 cache, so it lives in the same buffer
+TowerWH tower_wh(const rb200_mlp_layout* L, const float* ws, bool value) {
+  const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;  // elements
+  const int64_t per_tower = n0 + 2 * nn;                                // floats (hi + lo = 4 bytes per element)
+  const float* b = ws + (value ? 0 : per_tower);
+  TowerWH t;
+  t.w0h = b; t.w0l = b + n0 / 2;
+  t.w1h = b + n0; t.w1l = t.w1h + nn / 2;
+  t.w2h = b + n0 + nn; t.w2l = t.w2h + nn / 2;
+  return t;
+}
 }  // namespace
 
 // Refresh the exact-TF32 (hi, lo) weight copies the tensor-core GEMMs read. Call after every parameter update
@@ -535,6 +634,20 @@ extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float*
   if (e) return e;
   if (!params || !wsplit) return RB200_E_NULL;
   cudaStream_t st = rb::as_stream(stream);
+  if (half_mode()) {  // fp16 (hi, lo) of w * 2^10 for all hidden matrices: ONE launch (round 1: 20 kernels)
+    rb::tch::SplitSpec sp[6];
+    int cnt = 0;
+    for (int v = 0; v < 2; ++v) {
+      if (v == 0 && L->value_dim == 0) continue;
+      const TowerW w = tower_w(L, params, v == 0);
+      const TowerWH t = tower_wh(L, wsplit, v == 0);
+      const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;
+      sp[cnt++] = rb::tch::SplitSpec{w.w0, const_cast<float*>(t.w0h), const_cast<float*>(t.w0l), n0};
+      sp[cnt++] = rb::tch::SplitSpec{w.w1, const_cast<float*>(t.w1h), const_cast<float*>(t.w1l), nn};
+      sp[cnt++] = rb::tch::SplitSpec{w.w2, const_cast<float*>(t.w2h), const_cast<float*>(t.w2l), nn};
+    }
+    return rb::tch::split_weights(sp, cnt, st);
+  }
   for (int v = 0; v < 2; ++v) {
     if (v == 0 && L->value_dim == 0) continue;
     const TowerW w = tower_w(L, params, v == 0);
@@ -565,11 +678,18 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_layout* L, const float* params,
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3, st)))
-    return e;
-  if (values &&
-      (e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, G3, st)))
-    return e;
+  if (wsplit && half_mode()) {
+    TowerIO t[2] = {};
+    t[0].w = tower_w(L, P, false); t[0].wh = tower_wh(L, wsplit, false); t[0].H1 = H1; t[0].H2 = H2; t[0].H3 = H3;
+    t[1].w = tower_w(L, P, true);  t[1].wh = tower_wh(L, wsplit, true);  t[1].H1 = G1; t[1].H2 = G2; t[1].H3 = G3;
+    if ((e = towers_forward_h(states, idx, n, L->obs_dim, t, values ? 2 : 1, st))) return e;
+  } else {
+    if ((e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3, st)))
+      return e;
+    if (values &&
+        (e = tower_forward(states, idx, n, L->obs_dim, tower_w(L, P, true), wsplit ? &vws : nullptr, G1, G2, G3, st)))
+      return e;
+  }
   HeadFwdArgs h{};
   h.h3 = H3; h.g3 = values ? G3 : nullptr; h.mw = P + L->mw; h.mb = P + L->mb;
   h.logstd = P + L->logstd; h.vw3 = P + L->vw3; h.action = action; h.idx = idx; h.sample_mode = 0; h.mean_out = mean;
@@ -602,6 +722,14 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   h.g_mw = G + L->mw; h.g_mb = G + L->mb; h.g_logstd = G + L->logstd; h.g_vw3 = G + L->vw3;
   h.g_b2 = G + L->bb2; h.g_vb2 = G + L->vb2;
   h.n = n; h.act = L->act_dim; h.vdim = L->value_dim;
+  const bool use_h = wsplit && half_mode();
+  float* amax = work + 6 * PF;  // 8 floats of the scratch tail: max|dZ3|,|dZ2|,|dZ1| of the policy tower, then the value tower
+  if (use_h) {
+    cudaError_t ce = cudaMemsetAsync(amax, 0, 8 * sizeof(float), st);
+    if (ce != cudaSuccess) return (int)ce;
+    h.amax_dz3 = amax;
+    h.amax_dy3 = amax + 3;
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * (L->act_dim + L->value_dim) * kH + 64 + 2 * kH);
   const bool reg = L->act_dim <= 8 && L->value_dim <= 2;
   if (smem > 48 * 1024) {
@@ -617,6 +745,18 @@ extern "C" int rb200_mlp_backward(const rb200_mlp_layout* L, const float* params
   {
     cudaError_t ce = cudaPeekAtLastError();
     if (ce != cudaSuccess) return (int)ce;
+  }
+  if (use_h) {
+    TowerIO t[2] = {};
+    t[0].w = tower_w(L, P, false); t[0].wh = tower_wh(L, wsplit, false);
+    t[0].H1 = const_cast<float*>(H1); t[0].H2 = const_cast<float*>(H2); t[0].dZ3 = dZ3; t[0].tA = tA; t[0].tB = tB;
+    t[0].g_w0 = G + L->bw0; t[0].g_b0 = G + L->bb0; t[0].g_w1 = G + L->bw1; t[0].g_b1 = G + L->bb1;
+    t[0].g_w2 = G + L->bw2; t[0].g_b2 = G + L->bb2; t[0].amax = amax;
+    t[1].w = tower_w(L, P, true); t[1].wh = tower_wh(L, wsplit, true);
+    t[1].H1 = const_cast<float*>(G1); t[1].H2 = const_cast<float*>(G2); t[1].dZ3 = dY3; t[1].tA = uA; t[1].tB = uB;
+    t[1].g_w0 = G + L->vw0; t[1].g_b0 = G + L->vb0; t[1].g_w1 = G + L->vw1; t[1].g_b1 = G + L->vb1;
+    t[1].g_w2 = G + L->vw2; t[1].g_b2 = G + L->vb2; t[1].amax = amax + 3;
+    return towers_backward_h(states, idx, n, L->obs_dim, t, d_values ? 2 : 1, st);
   }
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
@@ -670,8 +810,15 @@ extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, 
   const float* P = params;
   const TowerWS bws = wsplit ? tower_ws(L, wsplit, false) : TowerWS{};
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
+  const bool use_h = wsplit != nullptr && half_mode();
+  if (use_h) {  // both towers in one grouped launch per layer (no side stream needed)
+    TowerIO t[2] = {};
+    t[0].w = tower_w(L, P, false); t[0].wh = tower_wh(L, wsplit, false); t[0].H1 = H1; t[0].H2 = H2; t[0].H3 = H3;
+    t[1].w = tower_w(L, P, true);  t[1].wh = tower_wh(L, wsplit, true);  t[1].H1 = G1; t[1].H2 = G2; t[1].H3 = G3;
+    if ((e = towers_forward_h(states, nullptr, n, L->obs_dim, t, values ? 2 : 1, st))) return e;
+  }
   // few tiles per GEMM -> run the two towers side by side
-  const bool fork = values != nullptr && wsplit != nullptr && n <= (int64_t)64 * rb::sm_count();
+  const bool fork = !use_h && values != nullptr && wsplit != nullptr && n <= (int64_t)64 * rb::sm_count();
   SideStream* ss = nullptr;
   if (fork) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -691,13 +838,13 @@ extern "C" int rb200_mlp_sample(const rb200_mlp_layout* L, const float* params, 
     ce = cudaEventRecord(ss->join, ss->s);
     if (ce != cudaSuccess) return (int)ce;
   }
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2, H3,
-                         st)))
+  if (!use_h && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, false), wsplit ? &bws : nullptr, H1, H2,
+                                   H3, st)))
     return e;
   if (ss) {
     cudaError_t ce = cudaStreamWaitEvent(st, ss->join, 0);
     if (ce != cudaSuccess) return (int)ce;
-  } else if (values && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true),
+  } else if (!use_h && values && (e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, P, true),
                                           wsplit ? &vws : nullptr, G1, G2, G3, st))) {
     return e;
   }
@@ -743,9 +890,14 @@ extern "C" int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, c
   const int64_t PF = act_floats(n);
   float *G1 = work, *G2 = G1 + PF, *G3 = G2 + PF;
   const TowerWS vws = wsplit ? tower_ws(L, wsplit, true) : TowerWS{};
-  if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, params, true), wsplit ? &vws : nullptr, G1, G2, G3,
-                         st)))
+  if (wsplit && half_mode()) {
+    TowerIO t[1] = {};
+    t[0].w = tower_w(L, params, true); t[0].wh = tower_wh(L, wsplit, true); t[0].H1 = G1; t[0].H2 = G2; t[0].H3 = G3;
+    if ((e = towers_forward_h(states, nullptr, n, L->obs_dim, t, 1, st))) return e;
+  } else if ((e = tower_forward(states, nullptr, n, L->obs_dim, tower_w(L, params, true), wsplit ? &vws : nullptr, G1, G2,
+                                G3, st))) {
     return e;
+  }
   value_head_kernel<<<head_grid(n), 256, 0, st>>>(G3, params + L->vw3, values, n, L->value_dim);
   rb::count_launch();
   RB_RETURN_LAUNCH();

@@ -38,4 +38,38 @@ int split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st);
 int split_transpose(const float* x, float* hi, float* lo, int R, int C, cudaStream_t st);
 
 }  // namespace tc
+
+// ---- round 2: fp16-split tensor-core GEMMs (tc_gemm_h.cu), grouped over up to two towers per launch -------------------
+namespace tch {
+
+struct GemmLaunch {        // one group (tower) of a forward / dgrad launch
+  const float* a;          // [M,K] fp32 streamed operand (activations or activation gradients)
+  const float* b_hi;       // fp16 (hi, lo) copies of the weight matrix * 2^10, stored [256 out, K in] (split_weights)
+  const float* b_lo;
+  float* c;                // [M,256] fp32 result
+  const float* bias;       // EPI_BIAS_TANH
+  const float* h;          // EPI_TANHGRAD: previous activation [M,256]
+  float* colsum;           // EPI_TANHGRAD: [256] += column sums of the output, or NULL
+  const float* amax_in;    // device max|a| (gradient operands: scaled into fp16 range), or NULL
+  float* amax_out;         // EPI_TANHGRAD: atomicMax of |output| (feeds the next gradient GEMM), or NULL
+};
+struct WgradLaunch {
+  const float* z;          // [n,256] activation gradients
+  const float* h;          // [n,IN]  layer inputs
+  float* dW;               // [256,IN] +=
+  const float* amax_z;     // device max|z| or NULL
+};
+struct SplitSpec {
+  const float* src;
+  float* hi;               // n fp16 values (storage typed as float*: the cache lives in the fp32 wsplit buffer)
+  float* lo;
+  int64_t n;
+};
+
+// epi: rb::tc::Epi.  b_mn = 0: C = epi(A . W^T) (forward, W [256,K]);  b_mn = 1: C = epi(A . W) (dgrad, W [256,256]).
+int launch(const GemmLaunch* groups, int ngroups, int64_t M, int K, int epi, int b_mn, cudaStream_t st);
+int wgrad(const WgradLaunch* groups, int ngroups, int64_t n, int IN, cudaStream_t st);
+int split_weights(const SplitSpec* specs, int count, cudaStream_t st);
+
+}  // namespace tch
 }  // namespace rb

@@ -1,0 +1,713 @@
+// K3 tensor-core path, round 2: fp32-accurate GEMMs on tcgen05 `kind::f16` through a 2-way fp16 split.
+//     a = a_hi + a_lo, b = b_hi + b_lo (fp16 numbers, 11 significant bits each; operands pre-scaled by a power of two so
+//     that both halves stay in fp16's normal range);  a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi   (dropped a_lo.b_lo ~ 2^-22)
+// Same three-MMA compensation as the round-1 3xTF32 kernels (tc_gemm.cu) with the same 2^-22 truncation, but
+//   * kind::f16 issues at twice the kind::tf32 rate, so an fp32-accurate product costs peak/3 instead of peak/6;
+//   * operands are 2 bytes in shared memory: the three MMAs re-read 72 KB per 128x256x32 k-block instead of 147 KB and
+//     the weight tiles TMA-fill 32 KB instead of 64 KB (round 1 was bound by exactly this shared-memory traffic);
+//   * the weight matrix is read K-major for the forward GEMM and MN-major for dgrad FROM THE SAME fp16 copy (UMMA
+//     descriptors select the major-ness), so the transposed weight copies and their 8 refresh kernels are gone;
+//   * one launch serves BOTH towers (policy backbone + value MLP have identical shapes): grouped tile scheduling halves
+//     the launches and fills the tail wave of small per-rank batches.
+// Activations / activation gradients stay plain fp32 in HBM (one copy); the streamed operand is TMA-landed as fp32
+// (SWIZZLE_128B) and split by transform warps into two fp16 SWIZZLE_64B tiles.  Gradients are tiny (1e-6 .. 1e-10):
+// their producer publishes max|x| and the consumer scales by 2^s (exact) so that the maximum sits at 2^13; the fp32
+// accumulator is scaled back in the epilogue (exact).
+// Reference op chains replaced: nn.Linear + tanh of MLPPolicy.backbone / ValueHead.mlp
+// (rlinf/models/embodiment/mlp_policy/mlp_policy.py:91-98, modules/value_head.py:37-45) and autograd's dgrad / wgrad.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include "tma.cuh"
+
+namespace rb {
+namespace tch {
+
+using rb::tc::BK;
+using rb::tc::BM;
+using rb::tc::BN;
+
+constexpr int kStages = 3;
+constexpr int kA32 = BM * BK * 4;   // 16 KB fp32 landing tile of the streamed operand
+constexpr int kA16 = BM * BK * 2;   //  8 KB per fp16 half
+constexpr int kB16 = BN * BK * 2;   // 16 KB per fp16 half of the weight tile
+constexpr int kStageBytes = kA32 + 2 * kA16 + 2 * kB16;  // 64 KB
+constexpr int kXfWarps = 4;
+constexpr int kThreads = 32 * (2 + kXfWarps + 4);  // producer, MMA, transform, epilogue = 320
+constexpr int kStagingBytes = 4 * 2 * 4096;
+constexpr int kTmemCols = 512;
+constexpr int kWeightScaleLog2 = 10;  // weights are stored as fp16 (hi, lo) of w * 2^10 (|w| <~ 1: both halves normal)
+
+// ---- PTX wrappers (same instructions as tc_gemm.cu) ---------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp; canonical layouts in
+//      cute/atom/mma_traits_sm100.hpp:167-203).  start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
+//      layout_type [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B ------------------------------------------------------------
+// K-major, SWIZZLE_64B: rows of 32 fp16 (64 B), 8-row groups 512 B apart (LBO unused for swizzled K-major).
+__device__ __forceinline__ uint64_t desc_k_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// MN-major, SWIZZLE_128B: ((8,n),(8,k)) in 16-byte units = 64 fp16 along MN per row (128 B), 8 K-rows per atom (SBO = 1024 B
+// between atoms along K), MN groups of 64 elements LBO bytes apart.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// MN-major, SWIZZLE_64B: ((4,n),(8,k)) = 32 fp16 along MN per row (64 B), 8 K-rows per atom (SBO = 512 B), MN groups LBO apart.
+__device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t addr, uint32_t lbo) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16 = 0 [7,10),[10,13),
+// a_major bit 15, b_major bit 16 (0 = K, 1 = MN), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
+// 2^s as a float (s in [-126, 127])
+__device__ __forceinline__ float pow2i(int s) { return __int_as_float((s + 127) << 23); }
+// power-of-two scale that brings max|x| = amax to [2^13, 2^14): fp16 keeps 11 bits for every |x| >= amax * 2^-27
+__device__ __forceinline__ int scale_log2_for(float amax) {
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+  if (!(amax > 0.0f) || e < -120) return 0;
+  int s = 13 - e;
+  return s > 100 ? 100 : (s < -100 ? -100 : s);
+}
+
+// fp32 [R rows x 32 floats] SWIZZLE_128B tile -> fp16 hi / lo [R rows x 32 halfs] SWIZZLE_64B tiles; item = (row, 8 floats)
+template <int NT>
+__device__ __forceinline__ void split_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                                           int rows, int t, float scale) {
+  const int items = rows * 4;
+#pragma unroll 2
+  for (int i = t; i < items; i += NT) {
+    const int r = i >> 2, cp = i & 3;
+    const uint8_t* srow = src + r * 128;
+    const float4 x0 = *reinterpret_cast<const float4*>(srow + (((2 * cp) ^ (r & 7)) << 4));
+    const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * cp + 1) ^ (r & 7)) << 4));
+    const float v[8] = {x0.x * scale, x0.y * scale, x0.z * scale, x0.w * scale,
+                        x1.x * scale, x1.y * scale, x1.z * scale, x1.w * scale};
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+    const int doff = r * 64 + ((cp ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(hi + doff) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + doff) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+struct __align__(16) Barriers {
+  uint64_t full[kStages];
+  uint64_t xf[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias[BN];  // forward: the layer bias; dgrad: per-CTA column sums of the output (bias gradient of the producer)
+};
+
+struct Group {
+  const float* bias;    // [256]                         (EPI_BIAS_TANH)
+  const float* h;       // [M,256] previous activation   (EPI_TANHGRAD)
+  float* colsum;        // [256] += column sums of the output, or NULL
+  const float* amax_in; // [1] max|A| published by A's producer (gradient GEMMs), or NULL = no scaling
+  float* amax_out;      // [1] atomicMax of |output| for the next gradient GEMM, or NULL
+};
+
+struct GemmParams {
+  CUtensorMap a[2], bh[2], bl[2], c[2];
+  Group g[2];
+  int64_t M;
+  int K;
+  int epi;
+  int b_mn;  // 0: weights K-major (forward), 1: MN-major (dgrad: B(n = in, k = out) = W[out][in])
+  int ngroups;
+  int flags;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* staging = smem + kStages * kStageBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(staging + kStagingBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x % P.ngroups;
+  const int cta = blockIdx.x / P.ngroups, n_cta = gridDim.x / P.ngroups;
+  const Group& G = P.g[grp];
+  const int64_t n_tiles = (P.M + BM - 1) / BM;
+  const int n_kb = P.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->xf[s], kXfWarps);
+      tma::mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tma::mbar_init(&bars->tmem_full[b], 1);
+      tma::mbar_init(&bars->tmem_empty[b], 4);
+    }
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kThreads) bars->bias[i] = (P.epi == rb::tc::EPI_BIAS_TANH) ? G.bias[i] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  // operand scaling: A by 2^sa (from the published amax), weights are stored * 2^kWeightScaleLog2
+  const int sa = G.amax_in ? scale_log2_for(__ldg(G.amax_in)) : 0;
+  const float a_scale = pow2i(sa);
+  const float out_scale = pow2i(-(sa + kWeightScaleLog2));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      tma::prefetch_desc(&P.a[grp]);
+      tma::prefetch_desc(&P.bh[grp]);
+      tma::prefetch_desc(&P.bl[grp]);
+      const int64_t my_tiles = n_tiles > cta ? (n_tiles - cta + n_cta - 1) / n_cta : 0;
+      const int64_t total = my_tiles * n_kb;
+      const int pf = 3;
+      for (int64_t j = 0; j < pf && j < total; ++j)
+        tma::prefetch_2d(&P.a[grp], (int)(j % n_kb) * BK, (int)((cta + (j / n_kb) * n_cta) * BM));
+      for (int64_t j = 0; j < total; ++j) {
+        const uint32_t it = (uint32_t)j;
+        const int kb = (int)(j % n_kb);
+        const int m0 = (int)((cta + (j / n_kb) * n_cta) * BM);
+        const int64_t jp = j + pf;
+        if (jp < total) tma::prefetch_2d(&P.a[grp], (int)(jp % n_kb) * BK, (int)((cta + (jp / n_kb) * n_cta) * BM));
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+        uint8_t* st = smem + s * kStageBytes;
+        uint8_t* sb = st + kA32 + 2 * kA16;
+        tma::mbar_arrive_expect_tx(&bars->full[s], kA32 + 2 * kB16);
+        tma::load_2d(st, &P.a[grp], kb * BK, m0, &bars->full[s]);  // rows >= M are zero-filled
+        if (!P.b_mn) {  // [256 rows x 32 k] boxes of the K-major weight copy
+          tma::load_2d(sb, &P.bh[grp], kb * BK, 0, &bars->full[s]);
+          tma::load_2d(sb + kB16, &P.bl[grp], kb * BK, 0, &bars->full[s]);
+        } else {        // MN-major: 4 boxes {64 in-columns, 32 out-rows} per half
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            tma::load_2d(sb + q * 4096, &P.bh[grp], q * 64, kb * BK, &bars->full[s]);
+            tma::load_2d(sb + kB16 + q * 4096, &P.bl[grp], q * 64, kb * BK, &bars->full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(BM, BN, 0, P.b_mn);
+      uint32_t it = 0, tcount = 0;
+      for (int64_t tile = cta; tile < n_tiles; tile += n_cta, ++tcount) {
+        const uint32_t buf = tcount & 1u;
+        const uint32_t bph = (tcount >> 1) & 1u;
+        tma::mbar_wait(&bars->tmem_empty[buf], bph ^ 1u);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          tma::mbar_wait(&bars->full[s], ph);
+          tma::mbar_wait(&bars->xf[s], ph);
+          fence_after_sync();
+          const uint32_t sa32 = tma::smem_u32(smem + s * kStageBytes);
+          const uint64_t a_hi = desc_k_sw64(sa32 + kA32), a_lo = desc_k_sw64(sa32 + kA32 + kA16);
+          const uint32_t sbase = sa32 + kA32 + 2 * kA16;
+          const uint64_t b_hi = P.b_mn ? desc_mn_sw128(sbase, 4096) : desc_k_sw64(sbase);
+          const uint64_t b_lo = P.b_mn ? desc_mn_sw128(sbase + kB16, 4096) : desc_k_sw64(sbase + kB16);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ka = (uint64_t)((k * 32) >> 4);                        // 16 fp16 = 32 B along a 64-B row
+            const uint64_t kbo = P.b_mn ? (uint64_t)((k * 2048) >> 4) : ka;       // MN-major: 16 K-rows of 128 B
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            mma_f16(d_tmem, a_lo + ka, b_hi + kbo, idesc, acc);  // small terms first
+            mma_f16(d_tmem, a_hi + ka, b_lo + kbo, idesc, 1u);
+            mma_f16(d_tmem, a_hi + ka, b_hi + kbo, idesc, 1u);
+          }
+          mma_commit(&bars->empty[s]);
+        }
+        mma_commit(&bars->tmem_full[buf]);
+      }
+    }
+  } else if (warp < 2 + kXfWarps) {
+    // ================= transform warps: fp32 A tile -> (A_hi, A_lo) fp16 tiles =================
+    const int t = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int64_t tile = cta; tile < n_tiles; tile += n_cta) {
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        tma::mbar_wait(&bars->full[s], ph);
+        uint8_t* st = smem + s * kStageBytes;
+        split_tile<32 * kXfWarps>(st, st + kA32, st + kA32 + kA16, BM, t, a_scale);
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;
+    const int ew = warp - (2 + kXfWarps);
+    float4 (*stg)[32][8] = reinterpret_cast<float4 (*)[32][8]>(staging + ew * 8192);
+    if (lane == 0) tma::prefetch_desc(&P.c[grp]);
+    const int rs = lane >> 3, c4 = lane & 7;
+    float4 hp[8];
+    auto load_h = [&](int64_t r0, int cc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t gr = r0 + i * 4 + rs;
+        hp[i] = gr < P.M ? __ldg(reinterpret_cast<const float4*>(G.h + gr * BN + cc) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (P.epi == rb::tc::EPI_TANHGRAD && (int64_t)cta < n_tiles) load_h((int64_t)cta * BM + q * 32, 0);
+    float vmax = 0.f;
+    uint32_t tcount = 0;
+    for (int64_t tile = cta; tile < n_tiles; tile += n_cta, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      const uint32_t bph = (tcount >> 1) & 1u;
+      tma::mbar_wait(&bars->tmem_full[buf], bph);
+      fence_after_sync();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      const int64_t row0 = tile * BM + q * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float4 (*sh)[8] = stg[(c0 >> 5) & 1];
+        if (lane == 0) tma::store_wait_read1();
+        __syncwarp();
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        if (P.epi == rb::tc::EPI_TANHGRAD) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rs;
+            sh[rr][c4 ^ (rr & 7)] = hp[i];
+          }
+          __syncwarp();
+          if (c0 + 32 < BN) load_h(row0, c0 + 32);
+          else if (tile + n_cta < n_tiles) load_h((tile + n_cta) * BM + q * 32, 0);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 v;
+          const float a0 = __uint_as_float(r[j4 * 4 + 0]) * out_scale, a1 = __uint_as_float(r[j4 * 4 + 1]) * out_scale;
+          const float a2 = __uint_as_float(r[j4 * 4 + 2]) * out_scale, a3 = __uint_as_float(r[j4 * 4 + 3]) * out_scale;
+          if (P.epi == rb::tc::EPI_STORE) {
+            v = make_float4(a0, a1, a2, a3);
+          } else if (P.epi == rb::tc::EPI_BIAS_TANH) {
+            const float4 b = *reinterpret_cast<const float4*>(&bars->bias[c0 + j4 * 4]);
+            v = make_float4(tanh_fast(a0 + b.x), tanh_fast(a1 + b.y), tanh_fast(a2 + b.z), tanh_fast(a3 + b.w));
+          } else {
+            const float4 h = sh[lane][j4 ^ (lane & 7)];
+            v = make_float4(a0 * (1.0f - h.x * h.x), a1 * (1.0f - h.y * h.y), a2 * (1.0f - h.z * h.z),
+                            a3 * (1.0f - h.w * h.w));
+            vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+          }
+          sh[lane][j4 ^ (lane & 7)] = v;
+        }
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma::store_2d(&P.c[grp], &sh[0][0], c0, (int)row0);  // rows >= M are clipped
+          tma::store_commit();
+        }
+        if (G.colsum != nullptr && P.epi == rb::tc::EPI_TANHGRAD) {
+          const int ch = lane >> 2, el = lane & 3;
+          float cs = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) cs += reinterpret_cast<const float*>(&sh[rr][ch ^ (rr & 7)])[el];
+          atomicAdd(&bars->bias[c0 + lane], cs);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(&bars->tmem_empty[buf]);
+    }
+    if (G.amax_out != nullptr && P.epi == rb::tc::EPI_TANHGRAD) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(G.amax_out), __float_as_uint(vmax));
+    }
+    if (lane == 0) tma::store_wait_all();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (G.colsum != nullptr && P.epi == rb::tc::EPI_TANHGRAD)
+    for (int i = threadIdx.x; i < BN; i += kThreads)
+      if (bars->bias[i] != 0.f) atomicAdd(G.colsum + i, bars->bias[i]);
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM:  dW[256, IN] += sum_m dZ[m, :]^T . H[m, :]     (IN % 32 == 0, <= 256), both operands MN-major.
+// Per k-block of 32 samples: TMA lands fp32 boxes {32 floats, 32 samples} (SWIZZLE_128B), 8 transform warps split them
+// into fp16 SWIZZLE_64B groups [32 samples x 32 features] = the canonical MN-major SW64 layout with LBO = 2048 B between
+// 32-feature groups and SBO = 512 B between 8-sample atoms; one K=16 MMA step spans two atoms (1024 B).
+// Grid = ngroups x 2 output tiles (128 rows of dW) x sample chunks; fp32 atomics into dW.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgStages = 2;
+constexpr int kWgA32 = 128 * BK * 4, kWgA16 = 128 * BK * 2;  // 16 KB / 8 KB
+constexpr int kWgB32 = 256 * BK * 4, kWgB16 = 256 * BK * 2;  // 32 KB / 16 KB (sized for IN = 256)
+constexpr int kWgStageBytes = kWgA32 + 2 * kWgA16 + kWgB32 + 2 * kWgB16;  // 96 KB
+constexpr int kWgXfWarps = 8;
+constexpr int kWgThreads = 32 * (2 + 4 + kWgXfWarps);
+
+struct WgBarriers {
+  uint64_t full[kWgStages], xf[kWgStages], empty[kWgStages], tmem_full;
+  uint32_t tmem_base, pad_;
+};
+
+struct WgradParams {
+  CUtensorMap z[2], h[2];
+  float* dW[2];
+  const float* amax_z[2];  // max|dZ| per group (or NULL)
+  int64_t n;
+  int IN, kb_per_chunk, ngroups;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  WgBarriers* bars = reinterpret_cast<WgBarriers*>(smem + kWgStages * kWgStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x % P.ngroups;
+  const int rest = blockIdx.x / P.ngroups;
+  const int out_tile = rest & 1, chunk = rest >> 1;
+  const int IN = P.IN;
+  const int n_kb_total = (int)((P.n + BK - 1) / BK);
+  const int kb0 = chunk * P.kb_per_chunk;
+  const int kb1 = (kb0 + P.kb_per_chunk < n_kb_total) ? kb0 + P.kb_per_chunk : n_kb_total;
+  const int n_kb = kb1 - kb0;
+  const int gB = IN / 32;
+  const uint32_t b32_bytes = (uint32_t)IN * BK * 4;
+  const uint32_t tmem_cols = IN <= 32 ? 32u : (IN <= 64 ? 64u : (IN <= 128 ? 128u : 256u));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      tma::mbar_init(&bars->full[s], 1);
+      tma::mbar_init(&bars->xf[s], kWgXfWarps);
+      tma::mbar_init(&bars->empty[s], 1);
+    }
+    tma::mbar_init(&bars->tmem_full, 1);
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int sz = P.amax_z[grp] ? scale_log2_for(__ldg(P.amax_z[grp])) : 0;
+  const float z_scale = pow2i(sz), out_scale = pow2i(-sz);
+
+  if (n_kb > 0) {
+    if (warp == 0) {
+      const int n_box = 4 + gB;
+      const int pf = 3;
+      if (lane < n_box)
+        for (int j = 0; j < pf && j < n_kb; ++j) {
+          if (lane < 4) tma::prefetch_2d(&P.z[grp], out_tile * 128 + lane * 32, (kb0 + j) * BK);
+          else tma::prefetch_2d(&P.h[grp], (lane - 4) * 32, (kb0 + j) * BK);
+        }
+      for (int it = 0; it < n_kb; ++it) {
+        if (lane < n_box && it + pf < n_kb) {
+          if (lane < 4) tma::prefetch_2d(&P.z[grp], out_tile * 128 + lane * 32, (kb0 + it + pf) * BK);
+          else tma::prefetch_2d(&P.h[grp], (lane - 4) * 32, (kb0 + it + pf) * BK);
+        }
+        const int s = it % kWgStages;
+        const uint32_t ph = (it / kWgStages) & 1u;
+        if (lane == 0) {
+          tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+          tma::mbar_arrive_expect_tx(&bars->full[s], kWgA32 + b32_bytes);
+        }
+        __syncwarp();
+        if (lane < n_box) {
+          uint8_t* st = smem + s * kWgStageBytes;
+          const int m0 = (kb0 + it) * BK;  // samples >= n are zero-filled
+          if (lane < 4) tma::load_2d(st + lane * 4096, &P.z[grp], out_tile * 128 + lane * 32, m0, &bars->full[s]);
+          else tma::load_2d(st + kWgA32 + 2 * kWgA16 + (lane - 4) * 4096, &P.h[grp], (lane - 4) * 32, m0, &bars->full[s]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = idesc_f16(128, IN, 1, 1);
+        for (int it = 0; it < n_kb; ++it) {
+          const int s = it % kWgStages;
+          const uint32_t ph = (it / kWgStages) & 1u;
+          tma::mbar_wait(&bars->xf[s], ph);  // implies full[s]
+          fence_after_sync();
+          const uint32_t sa = tma::smem_u32(smem + s * kWgStageBytes);
+          const uint32_t sb = sa + kWgA32 + 2 * kWgA16 + kWgB32;
+          const uint64_t a_hi = desc_mn_sw64(sa + kWgA32, 2048), a_lo = desc_mn_sw64(sa + kWgA32 + kWgA16, 2048);
+          const uint64_t b_hi = desc_mn_sw64(sb, 2048), b_lo = desc_mn_sw64(sb + kWgB16, 2048);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 1024) >> 4);  // next 16 samples = two 8-sample atoms
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            mma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, acc);
+            mma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+            mma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+          }
+          mma_commit(&bars->empty[s]);
+        }
+        mma_commit(&bars->tmem_full);
+      }
+    } else if (warp < 6) {
+      const int q = warp & 3;
+      tma::mbar_wait(&bars->tmem_full, 0);
+      fence_after_sync();
+      const int row = out_tile * 128 + q * 32 + lane;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* dW = P.dW[grp];
+      for (int c0 = 0; c0 < IN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        tmem_ld_wait();
+        float* dst = dW + (size_t)row * IN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + j),
+                    make_float4(__uint_as_float(r[j]) * out_scale, __uint_as_float(r[j + 1]) * out_scale,
+                                __uint_as_float(r[j + 2]) * out_scale, __uint_as_float(r[j + 3]) * out_scale));
+      }
+      fence_before_sync();
+    } else {
+      const int t = threadIdx.x - 6 * 32;
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % kWgStages;
+        const uint32_t ph = (it / kWgStages) & 1u;
+        tma::mbar_wait(&bars->full[s], ph);
+        uint8_t* st = smem + s * kWgStageBytes;
+        uint8_t* b32 = st + kWgA32 + 2 * kWgA16;
+        // groups of [32 samples x 32 floats] (4 KB) -> [32 samples x 32 halfs] (2 KB); consecutive groups are contiguous
+        // on both sides, so "rows" simply runs over groups * 32
+        split_tile<32 * kWgXfWarps>(st, st + kWgA32, st + kWgA32 + kWgA16, 4 * 32, t, z_scale);
+        split_tile<32 * kWgXfWarps>(b32, b32 + kWgB32, b32 + kWgB32 + kWgB16, gB * 32, t, 1.0f);
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---- weights -> fp16 (hi, lo) of w * 2^kWeightScaleLog2, all hidden matrices of the policy in ONE launch ----------------
+struct SplitJob {
+  const float* src;
+  __half* hi;
+  __half* lo;
+  int64_t n;
+};
+struct SplitJobs {
+  SplitJob j[8];
+  int count;
+};
+__global__ void __launch_bounds__(256) split_half_kernel(SplitJobs jobs) {
+  const float scale = (float)(1 << kWeightScaleLog2);
+  for (int q = 0; q < jobs.count; ++q) {
+    const SplitJob& J = jobs.j[q];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < J.n; i += stride) {
+      const float x = J.src[i] * scale;
+      const __half h = __float2half_rn(x);
+      J.hi[i] = h;
+      J.lo[i] = __float2half_rn(x - __half2float(h));
+    }
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+int encode_f32_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int encode_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+               int swizzle_bytes);
+
+int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn, cudaStream_t st) {
+  if (ngroups < 1 || ngroups > 2 || K % BK != 0 || K <= 0 || M <= 0) return RB200_E_SHAPE;
+  if (b_mn && K != BN) return RB200_E_SHAPE;  // dgrad of the square hidden layers
+  GemmParams P{};
+  P.M = M; P.K = K; P.epi = epi; P.b_mn = b_mn; P.ngroups = ngroups; P.flags = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const GemmLaunch& l = L[g];
+    const uintptr_t al = reinterpret_cast<uintptr_t>(l.a) | reinterpret_cast<uintptr_t>(l.b_hi) |
+                         reinterpret_cast<uintptr_t>(l.b_lo) | reinterpret_cast<uintptr_t>(l.c) |
+                         reinterpret_cast<uintptr_t>(l.h);
+    if (al & 15) return RB200_E_ALIGN;
+    int e = encode_f32_sw128(&P.a[g], l.a, (uint64_t)M, (uint64_t)K, BM);
+    if (!b_mn) {  // weights [256 out, K in] fp16, box {32 k, 256 rows}, SWIZZLE_64B
+      if (!e) e = encode_f16(&P.bh[g], l.b_hi, BN, (uint64_t)K, 32, BN, 64);
+      if (!e) e = encode_f16(&P.bl[g], l.b_lo, BN, (uint64_t)K, 32, BN, 64);
+    } else {      // weights [256 out = K rows, 256 in = N cols] fp16, box {64 in, 32 out}, SWIZZLE_128B
+      if (!e) e = encode_f16(&P.bh[g], l.b_hi, BN, BN, 64, 32, 128);
+      if (!e) e = encode_f16(&P.bl[g], l.b_lo, BN, BN, 64, 32, 128);
+    }
+    if (!e) e = encode_f32_sw128(&P.c[g], l.c, (uint64_t)M, BN, 32);
+    if (e) return RB200_E_UNSUPPORTED;
+    P.g[g] = Group{l.bias, l.h, l.colsum, l.amax_in, l.amax_out};
+  }
+  static bool attr_done = false;
+  constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
+  static_assert(kSmem <= 232448, "tc_h_gemm_kernel shared memory");
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_done = true;
+  }
+  const int64_t n_tiles = (M + BM - 1) / BM;
+  const int sms = rb::sm_count();
+  int per_group = sms / ngroups;
+  if (per_group > n_tiles) per_group = (int)n_tiles;
+  if (per_group < 1) per_group = 1;
+  tc_h_gemm_kernel<<<per_group * ngroups, kThreads, kSmem, st>>>(P);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st) {
+  if (ngroups < 1 || ngroups > 2 || n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
+  WgradParams P{};
+  P.n = n; P.IN = IN; P.ngroups = ngroups;
+  for (int g = 0; g < ngroups; ++g) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(L[g].z) | reinterpret_cast<uintptr_t>(L[g].h) |
+                         reinterpret_cast<uintptr_t>(L[g].dW);
+    if (al & 15) return RB200_E_ALIGN;
+    int e = encode_f32_sw128(&P.z[g], L[g].z, (uint64_t)n, 256, 32);
+    if (!e) e = encode_f32_sw128(&P.h[g], L[g].h, (uint64_t)n, (uint64_t)IN, 32);
+    if (e) return RB200_E_UNSUPPORTED;
+    P.dW[g] = L[g].dW;
+    P.amax_z[g] = L[g].amax_z;
+  }
+  static bool attr_done = false;
+  constexpr int kSmem = kWgStages * kWgStageBytes + 1024 + (int)sizeof(WgBarriers);
+  static_assert(kSmem <= 232448, "tc_h_wgrad_kernel shared memory");
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_h_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_done = true;
+  }
+  const int n_kb = (int)((n + BK - 1) / BK);
+  int chunks = rb::sm_count() / (2 * ngroups);
+  if (chunks < 1) chunks = 1;
+  if (chunks > n_kb) chunks = n_kb;
+  P.kb_per_chunk = (n_kb + chunks - 1) / chunks;
+  tc_h_wgrad_kernel<<<ngroups * 2 * chunks, kWgThreads, kSmem, st>>>(P);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int split_weights(const SplitSpec* specs, int count, cudaStream_t st) {
+  if (count < 1 || count > 8) return RB200_E_SHAPE;
+  SplitJobs jobs{};
+  jobs.count = count;
+  int64_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    jobs.j[i] = SplitJob{specs[i].src, reinterpret_cast<__half*>(specs[i].hi), reinterpret_cast<__half*>(specs[i].lo),
+                         specs[i].n};
+    total = specs[i].n > total ? specs[i].n : total;
+  }
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)rb::sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  split_half_kernel<<<(int)blocks, 256, 0, st>>>(jobs);
+  rb::count_launch();
+  cudaError_t ce = cudaPeekAtLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+}  // namespace tch
+}  // namespace rb
+
+// ---- unit-test entries (tests/test_gpu_tc_gemm.py) --------------------------------------------------------------------
+// C[M,256] = A[M,K] . B[256,K]^T (mode 0, forward) or A[M,256] . B[256,256] (mode 1, dgrad form: B is [out=K, in=N]);
+// work: >= 256*K floats (fp16 hi/lo copies of B).  amax (device float, nullable) exercises the gradient scaling.
+extern "C" int rb200_tc_gemm_h(const float* A, const float* B, float* C, int64_t M, int K, int mode, const float* amax,
+                               float* work, rb200_stream_t stream) {
+  if (!A || !B || !C || !work) return RB200_E_NULL;
+  if (M <= 0 || K <= 0 || K % rb::tc::BK != 0) return RB200_E_SHAPE;
+  cudaStream_t st = rb::as_stream(stream);
+  const int64_t nb = (int64_t)rb::tc::BN * K;
+  rb::tch::SplitSpec sp{B, work, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + nb * 2), nb};
+  int e = rb::tch::split_weights(&sp, 1, st);
+  if (e) return e;
+  rb::tch::GemmLaunch l{};
+  l.a = A; l.b_hi = sp.hi; l.b_lo = sp.lo; l.c = C; l.amax_in = amax;
+  return rb::tch::launch(&l, 1, M, K, rb::tc::EPI_STORE, mode ? 1 : 0, st);
+}
+
+extern "C" int rb200_tc_wgrad_h(const float* Z, const float* H, float* dW, int64_t n, int IN, const float* amax,
+                                rb200_stream_t stream) {
+  if (!Z || !H || !dW) return RB200_E_NULL;
+  rb::tch::WgradLaunch l{Z, H, dW, amax};
+  return rb::tch::wgrad(&l, 1, n, IN, rb::as_stream(stream));
+}

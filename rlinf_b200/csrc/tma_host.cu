@@ -63,4 +63,26 @@ int encode_sw128_box32(CUtensorMap* out, const float* base, uint64_t rows, uint6
 }
 }  // namespace tc
 
+namespace tch {
+// fp32 [rows, cols] row-major, box [box_rows x 32 floats], SWIZZLE_128B (landing tiles of the fp16-split kernels)
+int encode_f32_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return tc::encode_sw128(out, base, rows, cols, box_rows);
+}
+// fp16 [rows, cols] row-major, box [box_rows x box_cols], SWIZZLE_64B / SWIZZLE_128B (pre-split weight copies)
+int encode_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+               int swizzle_bytes) {
+  auto enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2ull};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+}  // namespace tch
+
 }  // namespace rb

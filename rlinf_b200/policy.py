@@ -32,7 +32,10 @@ class MLPPolicy:
         L.check(lib.rb200_mlp_layout_init(C.byref(self.layout), self.obs_dim, self.act_dim, self.value_dim, HIDDEN),
                 "mlp_layout_init")
         n = self.layout.total
-        self.flat_params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        # 4 spare floats behind the parameters: slot n carries the weight VERSION in the parameter broadcast
+        # (rlinf_b200/weight_sync.py: one NCCL broadcast of [params | version])
+        self._param_store = torch.zeros(n + 4, dtype=torch.float32, device=self.device)
+        self.flat_params = self._param_store[:n]
         self.flat_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._spec = self._build_spec()
         self._scratch: dict[tuple, torch.Tensor] = {}
@@ -69,6 +72,10 @@ class MLPPolicy:
 
     def state_dict(self):
         return {k: v.clone() for k, v in self.named_parameters()}
+
+    def sync_buffer(self) -> torch.Tensor:
+        """[flat parameters | version slot]: the tensor weight_sync.broadcast_flat sends."""
+        return self._param_store[: self.flat_params.numel() + 1]
 
     def mark_params_changed(self):
         """Call after flat_params was modified (optimiser step, load, broadcast)."""

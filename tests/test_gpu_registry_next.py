@@ -245,3 +245,38 @@ def test_rollout_buffer_trajectory_views_vs_reference_builder(golden):
         ab = buf.as_batch()
         for k in ("rewards", "dones", "prev_values", "prev_logprobs"):
             assert torch.equal(ab[k].cpu(), batch[k].cpu()), k
+
+
+def test_bucket_weight_sync_wire_format_round_trip(golden):
+    """f1: actor -> rollout hand-off in BucketWeightSyncer's wire format: bucket layout + metadata equal the reference's
+    (golden), payloads are views of the flat buffer, and a receiver policy ends up with identical parameters and the
+    version; bf16 transport casts and comes back within bf16 rounding."""
+    from rlinf_b200.policy import MLPPolicy
+    from rlinf_b200.weight_sync import SYNCER_VERSION_KEY, TOTAL_BUCKETS_KEY, BucketWeightSync
+
+    g = golden("r2")
+    src, dst = MLPPolicy(128, 8, seed=1), MLPPolicy(128, 8, seed=2)
+    assert [n for n, _ in src.named_parameters()] == [str(n) for n in g["bk_names"]]
+    for tag, size, dt in (("200k", 200 * 1024, None), ("1k", 1024, None), ("bf16_300k", 300 * 1024, torch.bfloat16)):
+        tx, rx = BucketWeightSync(src, size, dt), BucketWeightSync(dst, size, dt)
+        buckets = list(tx.iter_buckets(version=7))
+        layout = ["|".join(k for k in b if k not in (TOTAL_BUCKETS_KEY, SYNCER_VERSION_KEY)) for b in buckets]
+        assert layout == [str(x) for x in g[f"bk_{tag}_layout"]], tag
+        assert int(buckets[0][TOTAL_BUCKETS_KEY]) == int(g[f"bk_{tag}_total"]) == len(buckets)
+        assert int(buckets[0][SYNCER_VERSION_KEY]) == 7 and buckets[0][SYNCER_VERSION_KEY].dtype == torch.int32
+        if dt is None:  # zero-copy payload
+            assert buckets[-1]["actor_mean.bias"].untyped_storage().data_ptr() == src.flat_params.untyped_storage().data_ptr()
+        dst.flat_params.zero_()
+        it = iter(buckets)
+        assert rx.apply(lambda: next(it)) == 7
+        if dt is None:
+            assert torch.equal(dst.flat_params, src.flat_params)
+        else:
+            torch.testing.assert_close(dst.flat_params, src.flat_params, rtol=2 ** -8, atol=1e-8)
+    # host-staged buckets (bucket_device = cpu in the reference) are accepted too; unknown keys are ignored (strict=False)
+    tx, rx = BucketWeightSync(src, 1 << 30), BucketWeightSync(dst, 1 << 30)
+    staged = [{k: v.cpu() for k, v in b.items()} for b in tx.iter_buckets(3)]
+    staged[0]["some.other.buffer"] = torch.zeros(3)
+    dst.flat_params.zero_()
+    it = iter(staged)
+    assert rx.apply(lambda: next(it)) == 3 and torch.equal(dst.flat_params, src.flat_params)
