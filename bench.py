@@ -52,7 +52,7 @@ def parse():
                     help="rb200_debug_set_flags value (experimental kernel variants; 0 = shipped kernels)")
     ap.add_argument("--graph-update", action="store_true",
                     help="experimental: replay one CUDA graph per optimiser step (actor.cuda_graph_update)")
-    ap.add_argument("--rollout", default="auto", choices=["auto", "fused", "graph"],
+    ap.add_argument("--rollout", default="auto", choices=["auto", "tc", "fused", "graph"],
                     help="rollout implementation: persistent fused kernel, per-kernel CUDA graph, or the library default")
     return ap.parse_args()
 
@@ -435,7 +435,7 @@ def run_ours(a):
     if a.debug_flags:
         lib.rb200_debug_set_flags(int(a.debug_flags))
     peaks = measured_peaks()
-    over = {} if a.rollout == "auto" else {"rollout.fused_kernel": a.rollout == "fused"}
+    over = {} if a.rollout == "auto" else {"rollout.fused_kernel": {"tc": "tc", "fused": True, "graph": False}[a.rollout]}
     if a.graph_update:
         over["actor.cuda_graph_update"] = True
     cfg = synthetic_ppo_config(B=a.B, T=a.T, obs_dim=a.obs, action_dim=a.act, update_epoch=a.update_epoch,

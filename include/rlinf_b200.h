@@ -357,6 +357,49 @@ int rb200_rollout_fused(const rb200_mlp_layout* L, const float* params, const fl
                         int max_episode_steps, int auto_reset, int bootstrap_on_done, double gamma, double p_term,
                         double noise_std, double reward_noise_std, rb200_stream_t stream);
 
+/* Persistent TENSOR-CORE rollout (csrc/rollout_tc.cu): same loop, buffers, row alignment and random streams as
+ * rb200_rollout_fused, but every hidden layer of both towers and the env's s.W_s product run on tcgen05 (kind::f16,
+ * 2-way fp16 split with fp32 accumulation, computed transposed: D[hidden unit, env] = W . X^T, 32 environments per CTA,
+ * activations handed from TMEM to the next layer's operand tile in shared memory); the truncation bootstrap
+ * V(final_obs) rides in 32 extra MMA columns of the next step's value tower.  The weights are streamed from a packed,
+ * pre-split, pre-swizzled copy (rb200_rollout_tc_pack_bytes bytes, 16-byte aligned) that rb200_rollout_tc_prepare()
+ * rebuilds from the flat parameters and the env's w_s [obs,obs] after every parameter update.
+ * rb200_rollout_tc_supported() == 0 iff hidden == 256, value_dim == 1, act_dim <= 8, obs_dim % 32 == 0, obs_dim <= 128.
+ * Replaces the same reference loop as rb200_rollout_fused (env_worker.py:1059-1349, huggingface_worker.py:678-781). */
+int rb200_rollout_tc_supported(const rb200_mlp_layout* L, int B);
+int64_t rb200_rollout_tc_pack_bytes(const rb200_mlp_layout* L);
+int rb200_rollout_tc_prepare(const rb200_mlp_layout* L, const float* params, const float* w_s, void* pack,
+                             rb200_stream_t stream);
+int rb200_rollout_tc(const rb200_mlp_layout* L, const float* params, const void* pack, const float* w_a,
+                     float* states, float* actions, float* logprobs, float* values, float* rewards,
+                     uint8_t* terminations, uint8_t* truncations, uint8_t* dones, float* final_obs,
+                     float* final_values, int32_t* elapsed, const float* policy_noise, const float* env_noise,
+                     const uint64_t* counter_policy, const uint64_t* counter_env, uint64_t seed_policy,
+                     uint64_t seed_env, uint64_t offset_policy, int T, int B, int max_episode_steps, int auto_reset,
+                     int bootstrap_on_done, double gamma, double p_term, double noise_std, double reward_noise_std,
+                     rb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * token log-probabilities and entropies straight from the logits (csrc/logits.cu).
+ * Replaces compute_logprobs_from_logits (rlinf/utils/utils.py:454-492, = -cross_entropy) and
+ * compute_entropy_from_logits (:495-512, = -sum p log p over log_softmax) together with what their callers do first:
+ * logits.div_(temperature) (workers/actor/fsdp_actor_worker.py:478) and the OpenVLA action-bin window, every logit
+ * outside [v_lo, v_hi) treated as -inf (models/embodiment/openvla_oft/rlinf/openvla_oft_action_model.py:546-551).
+ * logits: dtype 0 = fp32, 1 = bf16; row r lives at logits + (r / L) * batch_stride + (r % L) * row_stride (elements),
+ * so the `[:, -L-1:-1, :]` slice of a [bsz, S, V] tensor needs no copy.  Forward reads every logit once and writes
+ * logprob / entropy / lse [N] fp32 (entropy, lse nullable); backward reads the logits once more and writes
+ *   dlogits_i = inv_T * (g_lp * (1[i = target] - p_i) - g_H * p_i * (log p_i + H)),  0 outside the window,
+ * in the logits' dtype with its own strides d_batch_stride / d_row_stride (grad_logprob / grad_entropy nullable = zero). */
+int rb200_logits_logprob_entropy_fwd(const void* logits, int dtype, const int64_t* target, int64_t N, int64_t L,
+                                     int64_t batch_stride, int64_t row_stride, int V, int v_lo, int v_hi,
+                                     double inv_temperature, float* logprob, float* entropy, float* lse,
+                                     rb200_stream_t stream);
+int rb200_logits_logprob_entropy_bwd(const void* logits, int dtype, const int64_t* target, int64_t N, int64_t L,
+                                     int64_t batch_stride, int64_t row_stride, int V, int v_lo, int v_hi,
+                                     double inv_temperature, const float* lse, const float* entropy,
+                                     const float* grad_logprob, const float* grad_entropy, void* dlogits,
+                                     int64_t d_batch_stride, int64_t d_row_stride, rb200_stream_t stream);
+
 /* Value tower only: values [n,value_dim] = ValueHead(states). Used for the bootstrap value of
  * final observations (get_bootstrap_values, workers/rollout/hf/huggingface_worker.py:612-627). */
 int rb200_mlp_value(const rb200_mlp_layout* L, const float* params, const float* wsplit,

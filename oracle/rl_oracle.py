@@ -319,6 +319,41 @@ def normalize_from_stats(x, stats):
     return ((x.to(torch.float64) - mean) * torch.rsqrt(var.clamp_min(0.0) + 1e-5)).float()
 
 
+def logprobs_entropy_from_logits(logits, target, temperature=1.0, window=None, g_logprobs=None, g_entropy=None):
+    """Token log-probabilities and entropies from logits as the reference's callers compute them:
+    `logits / temperature` (workers/actor/fsdp_actor_worker.py:478), optional OpenVLA action-bin window - every logit
+    outside [lo, hi) set to -inf (models/embodiment/openvla_oft/rlinf/openvla_oft_action_model.py:546-551) - then
+    compute_logprobs_from_logits = -cross_entropy (rlinf/utils/utils.py:454-492) and compute_entropy_from_logits =
+    -sum(where(p > 0, p * logp, 0)) with logp = log_softmax (:495-512).  fp32 throughout, like the reference on fp32
+    logits.  With upstream gradients given, also returns d(sum g_lp*logp + g_h*H)/d logits in closed form:
+        inv_T * (g_lp * (onehot - p) - g_h * p * (logp + H))      (zero outside the window).
+    NOTE (reference quirk): autograd through the reference's entropy with -inf logits yields NaN for every in-window
+    logit (0 * -inf in the backward of p * logp); the closed form here is the finite mathematical gradient."""
+    z = logits.float() / temperature
+    V = z.shape[-1]
+    lo, hi = window if window is not None else (0, V)
+    inside = torch.zeros(V, dtype=torch.bool)
+    inside[lo:hi] = True
+    z = torch.where(inside, z, torch.full_like(z, -math.inf))
+    m = z.max(dim=-1, keepdim=True).values
+    lse = m + torch.log(torch.exp(z - m).sum(dim=-1, keepdim=True))
+    logp = z - lse
+    p = torch.exp(logp)
+    lp_t = torch.gather(logp, -1, target.unsqueeze(-1)).squeeze(-1)
+    ent = -torch.where(p > 0, p * logp, torch.zeros_like(p)).sum(dim=-1)
+    if g_logprobs is None and g_entropy is None:
+        return lp_t, ent
+    onehot = torch.zeros_like(z).scatter_(-1, target.unsqueeze(-1), 1.0)
+    grad = torch.zeros_like(z)
+    if g_logprobs is not None:
+        grad = grad + g_logprobs.unsqueeze(-1) * (onehot - p)
+    if g_entropy is not None:
+        safe_logp = torch.where(p > 0, logp, torch.zeros_like(logp))
+        grad = grad - g_entropy.unsqueeze(-1) * p * (safe_logp + ent.unsqueeze(-1))
+    grad = torch.where(inside, grad, torch.zeros_like(grad)) / temperature
+    return lp_t, ent, grad
+
+
 def adv_and_returns_embodied(adv_type, rewards, dones, values=None, loss_mask=None,
                              loss_mask_sum=None, gamma=1.0, gae_lambda=1.0, group_size=8,
                              reward_type="action_level", **kw):

@@ -124,6 +124,15 @@ SIGNATURES = {
     "rb200_rollout_fused_prepare": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p]),
     "rb200_rollout_fused": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 19 + [c_uint64] * 3 + [c_int] * 5 +
                             [c_double] * 4 + [c_void_p]),
+    "rb200_rollout_tc_supported": (c_int, [C.POINTER(MlpLayout), c_int]),
+    "rb200_rollout_tc_pack_bytes": (c_int64, [C.POINTER(MlpLayout)]),
+    "rb200_rollout_tc_prepare": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rb200_rollout_tc": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 18 + [c_uint64] * 3 + [c_int] * 5 +
+                         [c_double] * 4 + [c_void_p]),
+    "rb200_logits_logprob_entropy_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int,
+                                                 c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rb200_logits_logprob_entropy_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int,
+                                                 c_int, c_int, c_double] + [c_void_p] * 5 + [c_int64, c_int64, c_void_p]),
     "rb200_mlp_value": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rb200_synth_env_step": (c_int, [c_void_p] * 13 + [c_int] * 5 + [c_float] * 3 + [c_uint64, c_void_p, c_void_p]),
     "rb200_bootstrap_rewards": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),

@@ -132,16 +132,18 @@ __device__ __forceinline__ void split_tile(const uint8_t* __restrict__ src, uint
     const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * cp + 1) ^ (r & 7)) << 4));
     const float v[8] = {x0.x * scale, x0.y * scale, x0.z * scale, x0.w * scale,
                         x1.x * scale, x1.y * scale, x1.z * scale, x1.w * scale};
-    __half2 h[4], l[4];
+    uint32_t h[4], l[4];  // packed half2 words (no 16-byte reinterpretation of a 4-byte-aligned local array)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      const float2 hf = __half22float2(h[j]);
-      l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     const int doff = r * 64 + ((cp ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(hi + doff) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(lo + doff) = *reinterpret_cast<const uint4*>(l);
+    *reinterpret_cast<uint4*>(hi + doff) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + doff) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -153,7 +155,7 @@ struct __align__(16) Barriers {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  float bias[BN];  // forward: the layer bias; dgrad: per-CTA column sums of the output (bias gradient of the producer)
+  alignas(16) float bias[BN];  // (read as float4: with kStages = 3 the members above end at byte 120) forward: the layer bias; dgrad: per-CTA column sums of the output (bias gradient of the producer)
 };
 
 struct Group {

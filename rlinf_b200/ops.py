@@ -358,3 +358,86 @@ def sub(a, b) -> torch.Tensor:
     out = torch.empty_like(x)
     L.check(lib.rb200_sub(L.ptr(x), L.ptr(y), L.ptr(out), x.numel(), L.stream_ptr()), "sub")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# log-probabilities / entropies from logits (csrc/logits.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _logits_geometry(logits: torch.Tensor):
+    """(tensor, N, L, batch_stride, row_stride, V) of a [..., V] tensor whose last dim is contiguous; [bsz, L, V] slices
+    such as `logits[:, -L-1:-1, :]` are addressed in place (no copy), anything else is made contiguous first."""
+    V = logits.shape[-1]
+    if logits.dim() == 3 and logits.stride(2) == 1 and logits.is_cuda:
+        bsz, Lr, _ = logits.shape
+        return logits, bsz * Lr, Lr, logits.stride(0), logits.stride(1), V
+    x = L.to_device(logits).reshape(-1, V).contiguous()
+    return x, x.shape[0], x.shape[0], 0, V, V
+
+
+def _raw_ptr(t: torch.Tensor):
+    return C.c_void_p(t.data_ptr())
+
+
+class _LogitsLogprobEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, temperature, window, want_entropy):
+        lib = L.load()
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"logits must be float32 or bfloat16, got {logits.dtype}")
+        x, N, Lr, bs, rs, V = _logits_geometry(logits)
+        tgt = L.to_device(target, x.device, torch.int64).reshape(-1).contiguous()
+        if tgt.numel() != N:
+            raise ValueError(f"target has {tgt.numel()} entries for {N} logit rows")
+        lo, hi = (0, V) if window is None else (int(window[0]), int(window[1]))
+        lp = torch.empty(N, dtype=torch.float32, device=x.device)
+        ent = torch.empty(N, dtype=torch.float32, device=x.device) if want_entropy else None
+        lse = torch.empty(N, dtype=torch.float32, device=x.device)
+        dt = 0 if x.dtype == torch.float32 else 1
+        L.check(lib.rb200_logits_logprob_entropy_fwd(_raw_ptr(x), dt, L.ptr(tgt), N, Lr, bs, rs, V, lo, hi,
+                                                     1.0 / float(temperature), L.ptr(lp), L.ptr(ent), L.ptr(lse),
+                                                     L.stream_ptr(x.device)), "logits_logprob_entropy_fwd")
+        ctx.save_for_backward(x, tgt, lse, ent if want_entropy else lse)
+        ctx.meta = (N, Lr, bs, rs, V, lo, hi, float(temperature), dt, want_entropy, tuple(logits.shape))
+        shape = logits.shape[:-1]
+        if want_entropy:
+            return lp.view(shape), ent.view(shape)
+        none = lp.new_zeros(())
+        ctx.mark_non_differentiable(none)
+        return lp.view(shape), none
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent):
+        lib = L.load()
+        x, tgt, lse, ent = ctx.saved_tensors
+        N, Lr, bs, rs, V, lo, hi, temp, dt, want_entropy, shape = ctx.meta
+        glp = g_lp.reshape(-1).float().contiguous() if g_lp is not None else None
+        gh = g_ent.reshape(-1).float().contiguous() if (want_entropy and g_ent is not None) else None
+        dx = torch.empty((N, V), dtype=x.dtype, device=x.device)  # contiguous gradient, whatever the logits' strides
+        L.check(lib.rb200_logits_logprob_entropy_bwd(_raw_ptr(x), dt, L.ptr(tgt), N, Lr, bs, rs, V, lo, hi, 1.0 / temp,
+                                                     L.ptr(lse), L.ptr(ent) if gh is not None else None, L.ptr(glp),
+                                                     L.ptr(gh), L.ptr(dx), Lr * V, V, L.stream_ptr(x.device)),
+                "logits_logprob_entropy_bwd")
+        return dx.view(shape), None, None, None, None
+
+
+def logprobs_entropy_from_logits(logits, target, temperature: float = 1.0, window=None, compute_entropy: bool = True):
+    """compute_logprobs_from_logits + compute_entropy_from_logits (rlinf/utils/utils.py:454-512) of `logits / temperature`
+    (fsdp_actor_worker.py:478) restricted to the vocabulary window [lo, hi) (OpenVLA action bins,
+    openvla_oft_action_model.py:546-551) in ONE pass over the logits, differentiable w.r.t. the raw logits.
+    Returns (logprobs [...], entropy [...] or None), fp32."""
+    lp, ent = _LogitsLogprobEntropy.apply(logits, target, temperature, window, bool(compute_entropy))
+    return lp, (ent if compute_entropy else None)
+
+
+def compute_logprobs_from_logits(logits, target, op_type: str = "torch"):
+    """Drop-in for rlinf.utils.utils.compute_logprobs_from_logits (:454-492); `op_type` is accepted and ignored (the
+    reference's flash_attn / liger variants compute the same quantity)."""
+    return logprobs_entropy_from_logits(logits, target, compute_entropy=False)[0]
+
+
+def compute_entropy_from_logits(logits, dim: int = -1):
+    """Drop-in for rlinf.utils.utils.compute_entropy_from_logits (:495-512), last-dim only."""
+    if dim not in (-1, logits.dim() - 1):
+        raise ValueError("compute_entropy_from_logits: only the last (vocabulary) dimension is supported")
+    tgt = torch.zeros(logits.shape[:-1], dtype=torch.int64, device=logits.device)
+    return logprobs_entropy_from_logits(logits, tgt, compute_entropy=True)[1]

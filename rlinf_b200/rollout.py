@@ -12,8 +12,9 @@ are written by the kernels directly into one `[T(+1), B, ...]` buffer in HBM - t
 Row alignment (env_worker.py:1120-1202): row t holds the action/logprob/value computed from obs_t,
 `dones[t]` = done flags produced by step t-1 (row 0 all False), `rewards[t]` = reward of step t with the
 truncation bootstrap gamma*V(final_obs) already folded in.
-Two implementations of the same loop: the persistent fused kernel (`rb200_rollout_fused`, one launch per rollout,
-default whenever it supports the problem; `rollout.fused_kernel: false` disables it) and the per-kernel loop
+Three implementations of the same loop: the persistent tensor-core kernel (`rb200_rollout_tc`, one launch per rollout,
+the default whenever it supports the problem), the persistent fp32 SIMT kernel (`rb200_rollout_fused`,
+`rollout.fused_kernel: true`) and the per-kernel loop (`rollout.fused_kernel: false`)
 captured once in a CUDA graph (rollout.enable_cuda_graph) and replayed - any env exposing `step_into` works there.
 """
 from __future__ import annotations
@@ -180,9 +181,21 @@ class RolloutWorker:
         # concurrently with the policy inference of step t+1 (both are 32-CTA GEMM chains on a 148-SM device)
         self._side = torch.cuda.Stream(device=policy.device) if policy.device.type == "cuda" else None
         # persistent fused kernel: needs the synthetic env's dynamics (w_s, w_a) and a supported MLP shape
-        mode = cfg.rollout.get("fused_kernel", "auto")  # True / False / "auto"
-        supported = (policy.device.type == "cuda" and hasattr(env, "w_s") and hasattr(env, "w_a")
+        # "auto" | "tc" (tensor-core persistent kernel) | True / "simt" (fp32 SIMT persistent kernel) | False (per-kernel graph)
+        mode = cfg.rollout.get("fused_kernel", "auto")
+        on_dev_env = policy.device.type == "cuda" and hasattr(env, "w_s") and hasattr(env, "w_a")
+        supported = (on_dev_env
                      and L.load().rb200_rollout_fused_supported(C.byref(policy.layout), int(buffer.B)) == 0)
+        tc_ok = (on_dev_env and L.load().rb200_rollout_tc_supported(C.byref(policy.layout), int(buffer.B)) == 0)
+        if mode == "tc" and not tc_ok:
+            raise ValueError("rollout.fused_kernel='tc' needs hidden 256, a value head, act_dim <= 8, obs_dim % 32 == 0 "
+                             "and obs_dim <= 128 (rb200_rollout_tc_supported)")
+        # tensor-core persistent kernel: one launch per rollout at any B (csrc/rollout_tc.cu) - the default when supported
+        self._tc = tc_ok and mode in ("auto", "tc")
+        if mode == "simt":
+            mode = True
+        if self._tc:
+            mode = False
         if mode == "auto":
             # measured (round 1, T = 512, ms per rollout fused / per-kernel graph): B = 512: 23 / 53, 1024: 33 / 55,
             # 2048: 46 / 55, 4096: 71 / 54 (88 before the register-tiled layer) - the fused kernel wins while a CTA owns <= 16 environments (small per-rank
@@ -211,9 +224,33 @@ class RolloutWorker:
         L.check(lib.rb200_counter_add(L.ptr(self.counter), buf.T, st), "counter_add")
         L.check(lib.rb200_counter_add(L.ptr(env.counter), buf.T, st), "counter_add")
 
+    def _tc_rollout(self, policy_noise=None, env_noise=None):
+        """The whole T-step loop in one persistent tcgen05 kernel (csrc/rollout_tc.cu)."""
+        lib = L.load()
+        buf, pol, env = self.buf, self.policy, self.env
+        st = L.stream_ptr()
+        lay = C.byref(pol.layout)
+        nbytes = int(lib.rb200_rollout_tc_pack_bytes(lay))
+        pack = pol._buf("rollout_tc_pack", (nbytes + 3) // 4)
+        L.check(lib.rb200_rollout_tc_prepare(lay, L.ptr(pol.flat_params), L.ptr(env.w_s), L.ptr(pack), st),
+                "rollout_tc_prepare")
+        L.check(lib.rb200_rollout_tc(
+            lay, L.ptr(pol.flat_params), L.ptr(pack), L.ptr(env.w_a), L.ptr(buf.states), L.ptr(buf.actions),
+            L.ptr(buf.prev_logprobs), L.ptr(buf.prev_values), L.ptr(buf.rewards), L.ptr(buf.terminations),
+            L.ptr(buf.truncations), L.ptr(buf.dones), L.ptr(buf.final_obs), L.ptr(buf.final_values),
+            L.ptr(env.elapsed), L.ptr(policy_noise), L.ptr(env_noise), L.ptr(self.counter), L.ptr(env.counter),
+            self.seed, env.seed, 0, buf.T, buf.B, env.max_episode_steps, int(self.auto_reset),
+            int(self.bootstrap_type != "standard"), self.gamma, env.p_term, env.noise_std, env.reward_noise_std, st),
+            "rollout_tc")
+        L.check(lib.rb200_counter_add(L.ptr(self.counter), buf.T, st), "counter_add")
+        L.check(lib.rb200_counter_add(L.ptr(env.counter), buf.T, st), "counter_add")
+
     def _one_rollout(self, policy_noise=None, env_noise=None):
         """policy_noise [T,B,act] / env_noise [T,B,2*obs+2]: pre-drawn N(0,1)/U(0,1) draws (parity tests);
         None -> Philox on the device."""
+        if self._tc:
+            return self._tc_rollout(None if policy_noise is None else policy_noise.contiguous(),
+                                    None if env_noise is None else env_noise.contiguous())
         if self._fused:
             if policy_noise is not None:
                 policy_noise = policy_noise.contiguous()
@@ -267,7 +304,7 @@ class RolloutWorker:
         else:
             buf.states[0].copy_(buf.states[buf.T])  # last obs of the previous rollout (bootstrap_step)
         # dones row 0 = zeros (env_worker.py:899-945): never written by the loop, stays zero
-        if self._fused or not self._use_graph or self._calls == 0:
+        if self._tc or self._fused or not self._use_graph or self._calls == 0:
             self._one_rollout()  # first call runs eagerly (also allocates every scratch buffer)
             self._calls += 1
             return
