@@ -10,7 +10,11 @@ Bs = [int(x) for x in sys.argv[1:]] or [512, 1024, 2048, 4096]
 T = 512
 for B in Bs:
     row = {}
-    for name, mode in (("tc", "tc"), ("fused", True), ("graph", False)):
+    import os
+    modes = (("tc", "tc"), ("fused", True), ("graph", False))
+    if os.environ.get("RB200_PROBE_MODES"):
+        modes = tuple(m for m in modes if m[0] in os.environ["RB200_PROBE_MODES"].split(","))
+    for name, mode in modes:
         cfg = synthetic_ppo_config(B=B, T=T, obs_dim=128, action_dim=8, **{"rollout.fused_kernel": mode})
         run = EmbodiedRunner(cfg)
         for _ in range(3):
