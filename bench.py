@@ -299,8 +299,9 @@ def run_reference(a):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r01_ncu_mlp_step_v3_table.txt, profiles/r01_ncu_gae_v4_summary.txt); only valid at the captured shape.
 NCU_TRAFFIC = {
-    ("tc_gemm_fwd", 262144): 485.4e6,   # 269.1 MB read + 216.3 MB written back before the kernel ends (rest stays in L2)
-    ("tc_wgrad", 262144): 541.6e6,
+    # profiles/r02_ncu_tc_h_kernels.txt: grouped (two-tower) launches at 262144 rows; per tower = half
+    ("tc_gemm_fwd", 262144): (537.5e6 + 483.3e6) / 2,   # 268.8 MB read + 241.6 MB written back before the kernel ends
+    ("tc_wgrad", 262144): (1075.3e6 + 4.4e6) / 2,
     ("gae_scan", 512, 4096): 18.9e6,    # reads only: the 16.8 MB of results are still in L2 when the kernel ends
 }
 
@@ -383,7 +384,7 @@ def kernel_rooflines(a, peaks, torch):
                                       "launch_note": "memset + main + finalise nodes; rollout rows gathered through idx"}
     del cur, idxs, old, adv, ret, pv, perm
 
-    # ---- tcgen05 3xTF32 GEMMs of the MLP towers at the mini-batch shape (tensor / shared-memory bound) ----
+    # ---- tcgen05 fp16-split GEMMs of the MLP towers at the mini-batch shape (the shipped kernels, csrc/tc_gemm_h.cu) ----
     n = mb
     K = 256
     Amat = torch.randn(n, K, device=dev)
@@ -396,24 +397,38 @@ def kernel_rooflines(a, peaks, torch):
 
     def gemm_all():
         for _ in range(reps_k):
-            L.check(lib.rb200_tc_gemm(L.ptr(Amat), L.ptr(Wmat), L.ptr(Cmat), n, K, L.ptr(wk), L.stream_ptr()), "tc_gemm")
+            L.check(lib.rb200_tc_gemm_h(L.ptr(Amat), L.ptr(Wmat), L.ptr(Cmat), n, K, 0, None, L.ptr(wk), L.stream_ptr()),
+                    "tc_gemm_h")
 
     def wgrad_all():
         for _ in range(reps_k):
-            L.check(lib.rb200_tc_wgrad(L.ptr(Z), L.ptr(Amat), L.ptr(dW), n, K, None, L.stream_ptr()), "tc_wgrad")
+            L.check(lib.rb200_tc_wgrad_h(L.ptr(Z), L.ptr(Amat), L.ptr(dW), n, K, None, L.stream_ptr()), "tc_wgrad_h")
 
     flops = 2.0 * n * 256 * K
-    ceiling = peaks["bf16_tflops"] / 6.0
+    ceiling = peaks["bf16_tflops"] / 3.0
+    bytes_gemm = n * K * 4 + n * 256 * 4
     for key, fn, note in (("tc_gemm_fwd", gemm_all, "C[n,256] = A[n,256] . W^T, plain fp32 in/out; launch includes the 3 us "
                                                     "weight-split kernel of the unit-test entry"),
                           ("tc_wgrad", wgrad_all, "dW[256,256] += Z[n,256]^T . H[n,256], fp32 atomics into dW")):
         t = time_graph(fn, reps_k)
-        out[key] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": flops / t / 1e12 / peaks["bf16_tflops"], "frac_of_3xtf32_ceiling": flops / t / 1e12 / ceiling,
+        out[key] = {"bound": "hbm", "achieved": bytes_gemm / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_gemm / t / 1e9 / peaks["hbm_gbs"],
+                    "tensor_tflops": flops / t / 1e12, "frac_of_fp16_split_ceiling": flops / t / 1e12 / ceiling,
                     "traffic": NCU_TRAFFIC.get((key, n)), "us_per_launch": t * 1e6, "algorithmic_flops": flops,
-                    "algorithmic_bytes": n * K * 4 + n * 256 * 4 if key == "tc_gemm_fwd" else n * K * 4 + n * 256 * 4,
-                    "hbm_gbs": (n * K * 4 + n * 256 * 4) / t / 1e9, "rows": n, "note": note}
+                    "algorithmic_bytes": bytes_gemm, "rows": n, "note": note}
     return out
+
+
+def _update_phase_bytes(n, obs, act, H):
+    """Algorithmic HBM bytes of ONE pass of the update over n samples (fp32; U = n*H*4 bytes = one [n,256] tensor):
+    forward: per tower read X (obs) + write H1 | read H1 write H2 | read H2 write H3; heads read H3, G3;
+    backward: heads read H3,G3 write dZ3 (both towers); per tower wgrad2 (dZ3,H2), dgrad2 (dZ3,H2 -> dZ2), wgrad1 (dZ2,H1),
+    dgrad1 (dZ2,H1 -> dZ1), wgrad0 (dZ1,X); loss / optimiser / small [n,act] tensors are < 1 %."""
+    U = n * H * 4
+    X = n * obs * 4
+    fwd = 2 * (X + U + 2 * U + 2 * U) + 2 * U
+    bwd = 4 * U + 2 * (2 * U + 3 * U + 2 * U + 3 * U + (U + X))
+    return fwd + bwd
 
 
 def run_ours(a):
@@ -561,16 +576,16 @@ def run_ours(a):
         bwd = 2 * (O * H + 2 * H * H) * 2 + 2 * (2 * H * H) * 2  # wgrad (3 layers) + dgrad (2 layers), two towers
         flops_update = (fwd + bwd) * n * a.update_epoch
         upd_s = (ms_per_step - rollout_ms) * 1e-3
-        ceiling = peaks["bf16_tflops_sustained"] / 6.0  # tf32 = 1/2 bf16 rate, 3 MMAs per logical product (3xTF32)
+        ceiling = peaks["bf16_tflops_sustained"] / 3.0  # fp32-accurate product = 3 kind::f16 MMAs
+        bytes_update = _update_phase_bytes(n, O, A, H) * a.update_epoch
         line["roofline"] = {
-            "kernel": "tc_gemm_kernel / tc_wgrad_kernel (tcgen05 kind::tf32, 3xTF32-compensated MLP GEMMs: forward, dgrad, "
-                      "wgrad) - the dominant kernels of the step",
-            "bound": "tensor", "achieved": flops_update / upd_s / 1e12, "peak": peaks["bf16_tflops_sustained"],
-            "unit": "TFLOP/s", "frac": flops_update / upd_s / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
-            "frac_of_3xtf32_ceiling": flops_update / upd_s / 1e12 / ceiling,
-            "note": f"logical fp32 GEMM flops of the whole update phase / update time (includes loss, heads, optimiser); "
-                    f"peak = {peaks['source']} bf16 sustained; fp32-accurate 3xTF32 costs 6x the bf16 tensor time, so the "
-                    f"ceiling for this path is peak/6 = {ceiling:.0f} TFLOP/s"}
+            "kernel": "whole update phase (tc_h_gemm_kernel / tc_h_wgrad_kernel fp16-split tcgen05 GEMMs + heads + loss + AdamW)",
+            "bound": "hbm", "achieved": bytes_update / upd_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": bytes_update / upd_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+            "algorithmic_bytes": bytes_update, "tensor_tflops": flops_update / upd_s / 1e12,
+            "frac_of_fp16_split_ceiling": flops_update / upd_s / 1e12 / ceiling,
+            "note": "algorithmic HBM bytes of the update phase (fp32 activations / gradients read and written once per GEMM, "
+                    "DESIGN.md section 4) / update time; the fp32 [n,256] activation traffic, not the tensor pipe, bounds it"}
         if not a.no_kernel_bench:
             log("kernel rooflines ...")
             try:
@@ -578,20 +593,18 @@ def run_ours(a):
                 g = kr.pop("tc_gemm_fwd")
                 w = kr.pop("tc_wgrad")
                 line["roofline_update_phase"] = line["roofline"]
-                # dominant kernel of the step, timed alone with CUDA events (burst peak)
+                # dominant kernel of the step, timed alone with CUDA events
                 line["roofline"] = {
-                    "kernel": "rb::tc::tc_gemm_kernel (tcgen05 kind::tf32, 3xTF32-compensated fp32 GEMM of the MLP towers; "
-                              "forward/dgrad), mini-batch shape",
-                    "bound": "tensor", "achieved": g["achieved"], "peak": g["peak"], "unit": "TFLOP/s", "frac": g["frac"],
+                    "kernel": "rb::tch::tc_h_gemm_kernel (tcgen05 kind::f16, 2-way fp16 split = fp32-accurate GEMM of the MLP "
+                              "towers; forward/dgrad), mini-batch shape, one tower",
+                    "bound": "hbm", "achieved": g["achieved"], "peak": g["peak"], "unit": "GB/s", "frac": g["frac"],
                     "traffic": g["traffic"], "algorithmic_bytes": g["algorithmic_bytes"],
-                    "frac_of_3xtf32_ceiling": g["frac_of_3xtf32_ceiling"],
+                    "tensor_tflops": g["tensor_tflops"], "frac_of_fp16_split_ceiling": g["frac_of_fp16_split_ceiling"],
                     "us_per_launch": g["us_per_launch"], "algorithmic_flops": g["algorithmic_flops"],
-                    "hbm_gbs": g["hbm_gbs"],
-                    "note": "achieved = logical fp32 flops (2*n*256*256) / live CUDA-event time per launch; peak = measured "
-                            "bf16 burst; an fp32-accurate product costs 3 kind::tf32 MMAs at half the bf16 rate, so the "
-                            "ceiling of this path is peak/6 (frac_of_3xtf32_ceiling). Per-launch shared-memory traffic "
-                            "(3 MMAs re-reading both operands + TMA fill + in-kernel hi/lo split) is what bounds it: "
-                            "~300 KB per 128x256x32 k-block at 128 B/clk/SM; see DESIGN.md section 4. " + g["note"]}
+                    "note": "achieved = algorithmic bytes (A [n,256] fp32 read + C [n,256] fp32 written) / live CUDA-event time "
+                            "per launch; peak = measured HBM copy bandwidth.  2*n*256*256 flops over 2 KB per row = 64 "
+                            "flop/B: at 3 kind::f16 MMAs per product the tensor time (peak/3) is below the HBM time of the "
+                            "fp32 operands, so HBM bounds the kernel (DESIGN.md section 4). " + g["note"]}
                 line["roofline_tc_wgrad"] = w
                 line["roofline_hbm_kernels"] = kr
             except Exception as e:  # pragma: no cover

@@ -334,6 +334,8 @@ int rb200_tc_wgrad_h(const float* Z, const float* H, float* dW, int64_t n, int I
  * hi part in shared memory (not needed: the tensor core truncates), bit 1 = fused-rollout variants with a 4-k-step weight
  * prefetch (experimental), bit 2 = cta_group::2 (CTA-pair) forward/dgrad GEMM (experimental), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
 int rb200_debug_set_flags(int flags);
+/* probe hook of the fp16-split GEMM (csrc/tc_gemm_h.cu): 16 int64 per-role wait / work cycle counters of CTA 0 */
+int rb200_tc_h_debug(void* prof16);
 
 /* Persistent fused rollout (csrc/rollout_fused.cu): the whole T-step loop of one rank - MLP actor/critic inference,
  * Normal sampling, synthetic-env dynamics with auto-reset and the truncation bootstrap of rewards - in ONE kernel;
@@ -367,6 +369,8 @@ int rb200_rollout_fused(const rb200_mlp_layout* L, const float* params, const fl
  * rb200_rollout_tc_supported() == 0 iff hidden == 256, value_dim == 1, act_dim <= 8, obs_dim % 32 == 0, obs_dim <= 128.
  * Replaces the same reference loop as rb200_rollout_fused (env_worker.py:1059-1349, huggingface_worker.py:678-781). */
 int rb200_rollout_tc_supported(const rb200_mlp_layout* L, int B);
+/* probe hook: ablation switches + 16 int64 wait-cycle counters of CTA 0 (flags = 0, prof16 = NULL: production kernel) */
+int rb200_rollout_tc_debug(int flags, void* prof16);
 int64_t rb200_rollout_tc_pack_bytes(const rb200_mlp_layout* L);
 int rb200_rollout_tc_prepare(const rb200_mlp_layout* L, const float* params, const float* w_s, void* pack,
                              rb200_stream_t stream);

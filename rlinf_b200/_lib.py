@@ -119,12 +119,14 @@ SIGNATURES = {
     "rb200_tc_gemm_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rb200_tc_wgrad_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "rb200_debug_set_flags": (c_int, [c_int]),
+    "rb200_tc_h_debug": (c_int, [c_void_p]),
     "rb200_rollout_fused_wt_floats": (c_int64, [C.POINTER(MlpLayout)]),
     "rb200_rollout_fused_supported": (c_int, [C.POINTER(MlpLayout), c_int]),
     "rb200_rollout_fused_prepare": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p]),
     "rb200_rollout_fused": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 19 + [c_uint64] * 3 + [c_int] * 5 +
                             [c_double] * 4 + [c_void_p]),
     "rb200_rollout_tc_supported": (c_int, [C.POINTER(MlpLayout), c_int]),
+    "rb200_rollout_tc_debug": (c_int, [c_int, c_void_p]),
     "rb200_rollout_tc_pack_bytes": (c_int64, [C.POINTER(MlpLayout)]),
     "rb200_rollout_tc_prepare": (c_int, [C.POINTER(MlpLayout), c_void_p, c_void_p, c_void_p, c_void_p]),
     "rb200_rollout_tc": (c_int, [C.POINTER(MlpLayout)] + [c_void_p] * 18 + [c_uint64] * 3 + [c_int] * 5 +

@@ -96,6 +96,8 @@ struct TcArgs {
   int T, B, obs, act;
   int max_episode_steps, auto_reset, bootstrap_on_done;
   float gamma, p_term, noise_std, reward_noise_std;
+  int dbg;               // ablation switches for tools/rollout_tc_probe.py (0 in production), see rb200_rollout_tc_debug
+  long long* prof;       // [16] wait-cycle counters of CTA 0 (PROF instantiation only)
 };
 
 // ---- PTX wrappers (same instructions as tc_gemm_h.cu) ---------------------------------------------------------------
@@ -179,7 +181,8 @@ __device__ __forceinline__ float dot256(const float* row, const float* w, int la
   return rb::warp_sum(s);
 }
 
-// weight-stream segments in stage units (one stage = one 128-row tile x one 32-wide k-block, hi | lo)
+// weight-stream segments in stage units (one stage = one 128-row tile x one 32-wide k-block, hi | lo; inside a layer
+// the stages are ordered k-block outer, M tile inner)
 struct Segs {
   int env, a0, v0, a1, v1, a2, v2, total, nkb0;
 };
@@ -197,6 +200,19 @@ __host__ __device__ inline Segs make_segs(int obs) {
   return s;
 }
 
+// wait on an mbarrier; the PROF instantiation accumulates the cycles spent waiting (tools/rollout_tc_probe.py)
+template <bool PROF>
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long& acc) {
+  if constexpr (PROF) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -246,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     const float v = (r < nE) ? p.states[(size_t)(e0 + r) * obs + c] : 0.f;
     store_split(obuf, (uint32_t)sg.nkb0 * 4096u, (uint32_t)(c >> 5) * 4096u + sw64_off(r, c & 31), v);
   }
+  for (int i = tid; i < kNE * kMaxActTc; i += kThreads) ms->act[i] = 0.f;
   if (tid < kNE) {
     ms->el[tid] = tid < nE ? p.elapsed[e0 + tid] : 0;
     ms->flag[tid] = 0;
@@ -256,6 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = ms->tmem_base;
+  long long pc[16];  // PROF: cycles spent per wait / section (dead code otherwise)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pc[i] = 0;
+  const long long t_start = PROF ? clock64() : 0;
+  const int dbg = PROF ? p.dbg : 0;  // ablations exist in the instrumented instantiation only
 
   if (warp == 0) {
     // ================= weight-stream producer =================
@@ -265,7 +287,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         for (int i = 0; i < n; ++i, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
-          mbar_wait(&ms->empty[s], ph ^ 1u);
+          wait_bar<PROF>(&ms->empty[s], ph ^ 1u, pc[0]);
+          if (dbg & 4) {  // ablation: no weight traffic (the ring keeps whatever it holds)
+            mbar_arrive(&ms->full[s]);
+            continue;
+          }
           rb::tma::mbar_arrive_expect_tx(&ms->full[s], kStageBytes);
           bulk_load(ring + s * kStageBytes, p.pack + (size_t)(stage0 + i) * kStageBytes, kStageBytes, &ms->full[s]);
         }
@@ -283,12 +309,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
       // one layer: D[tile m] (TMEM columns d_col + m*N) = W tile m [128 x 32*nkb] . operand[N rows x 32*nkb]^T
       auto seg = [&](int ntile, int nkb, uint32_t b_hi_addr, uint32_t b_half, uint32_t b_kb_stride, uint32_t d_col, int N) {
         const uint32_t idesc = idesc_f16(128, N);
-        for (int m = 0; m < ntile; ++m) {
-          const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(m * N);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+        // k-block outer, M tile inner: consecutive MMAs alternate between the two accumulator tiles, so the
+        // accumulate-into-the-same-tile dependency of these short (N = 32) MMAs overlaps with the other tile's
+        for (int kb = 0; kb < nkb; ++kb) {
+          for (int m = 0; m < ntile; ++m, ++it) {
+            const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(m * N);
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1u;
-            mbar_wait(&ms->full[s], ph);
+            wait_bar<PROF>(&ms->full[s], ph, pc[1]);
             fence_after_sync();
             const uint32_t sa = ring_a + s * kStageBytes;
             const uint64_t a_hi = desc_k_sw64(sa), a_lo = desc_k_sw64(sa + kHalfTile);
@@ -296,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
             const uint64_t b_hi = desc_k_sw64(sb), b_lo = desc_k_sw64(sb + b_half);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
+              if (dbg & 2) break;  // ablation: no tensor-core work
               const uint64_t ka = (uint64_t)(2 * k);  // 16 fp16 = 32 B along the 64-B row
               const uint32_t accf = (kb > 0 || k > 0) ? 1u : 0u;
               mma_f16(d_tmem, a_lo + ka, b_hi + ka, idesc, accf);  // small terms first
@@ -311,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
       for (int t = 0; t <= T; ++t) {
         const bool tail = (t == T);
         if (t > 0) {
-          mbar_wait(&ms->obs_ready, p_obs);
+          wait_bar<PROF>(&ms->obs_ready, p_obs, pc[2]);
           p_obs ^= 1u;
           fence_after_sync();
         }
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           mma_commit(&ms->acc_a);
         }
         if (t > 0) {  // accumulator columns of the value tower are free once the previous value head has read them
-          mbar_wait(&ms->vhead, p_vh);
+          wait_bar<PROF>(&ms->vhead, p_vh, pc[3]);
           p_vh ^= 1u;
           fence_after_sync();
         }
@@ -331,13 +360,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         mma_commit(&ms->acc_v);
         for (int l = 1; l < 3; ++l) {
           if (!tail) {
-            mbar_wait(&ms->opnd_a, p_oa);
+            wait_bar<PROF>(&ms->opnd_a, p_oa, pc[4]);
             p_oa ^= 1u;
             fence_after_sync();
             seg(2, 8, abuf_a, kAbufHalf, 2048u, kAccA, kNE);
             mma_commit(&ms->acc_a);
           }
-          mbar_wait(&ms->opnd_v, p_ov);
+          wait_bar<PROF>(&ms->opnd_v, p_ov, pc[5]);
           p_ov ^= 1u;
           fence_after_sync();
           seg(2, 8, vbuf_a, kVbufHalf, 4096u, kAccV, nv);
@@ -347,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     }
   } else if (warp < 6) {
     // ================= actor tower: epilogues, mean head, sampling =================
-    const int q = warp & 3, ew = warp - 2, gt = tid - 64;
+    const int q = warp & 3, gt = tid - 64;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + kAccA;
     float bias[3][2];
     {
@@ -360,15 +389,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     for (int t = 0; t < T; ++t) {
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
-        mbar_wait(&ms->acc_a, p_acc);
+        wait_bar<PROF>(&ms->acc_a, p_acc, pc[6]);
         p_acc ^= 1u;
         fence_after_sync();
+        const long long t_e0 = PROF ? clock64() : 0;
 #pragma unroll 1
         for (int m = 0; m < 2; ++m) {
           uint32_t r[32];
           tmem_ld32(tq + (uint32_t)(m * kNE), r);
           tmem_ld_wait();
           const float b = bias[l][m];
+          if (dbg & 8) continue;  // ablation: accumulator read only
           if (l < 2) {
             const uint32_t kb_off = (uint32_t)(m * 4 + q) * 2048u;  // hidden unit j = m*128 + q*32 + lane -> k-block j/32
 #pragma unroll
@@ -388,24 +419,29 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         } else {
           named_sync(1, 128);
         }
+        if constexpr (PROF) pc[13] += clock64() - t_e0;
       }
-      // ---- mean head: one warp per environment ----
-      for (int e = ew; e < kNE; e += 4) {
-        const float* row = h3 + e * kH;
-        float my = 0.f;
-        for (int a = 0; a < act; ++a) {
-          const float s = dot256(row, ms->mw + a * kH, lane);
-          if (lane == a) my = s + P[p.L.mb + a];
-        }
-        if (lane < act) ms->mean[e * kMaxActTc + lane] = my;
-      }
-      named_sync(1, 128);
-      // ---- Normal sample + log-prob, one (env, action) pair per thread ----
+      const long long t_h0 = PROF ? clock64() : 0;
+      // ---- mean head + Normal sample + log-prob: one (env, action) pair per thread.  Each thread does its own
+      //      256-long dot product (float4 reads rotated by the lane so that a warp touches every bank once): no
+      //      warp reductions, no shared-memory hand-off between head and sampling ----
       for (int i = gt; i < kNE * act; i += 128) {
         const int e = i / act, a = i - e * act;
+        const float4* hr = reinterpret_cast<const float4*>(h3 + e * kH);
+        const float4* wr = reinterpret_cast<const float4*>(ms->mw + a * kH);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) {
+          const int kk = (j + lane) & 63;
+          const float4 hv = hr[kk], wv = wr[kk];
+          s0 = fmaf(hv.x, wv.x, s0);
+          s1 = fmaf(hv.y, wv.y, s1);
+          s2 = fmaf(hv.z, wv.z, s2);
+          s3 = fmaf(hv.w, wv.w, s3);
+        }
+        const float mean = ((s0 + s1) + (s2 + s3)) + P[p.L.mb + a];
         if (e < nE) {
           const int64_t row = e0 + e;
-          const float mean = ms->mean[e * kMaxActTc + a];
           const float ls = P[p.L.logstd + a];
           const float sd = expf(ls);
           float z;
@@ -426,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         }
       }
       __syncwarp();
+      if constexpr (PROF) pc[14] += clock64() - t_h0;
       if (lane == 0) mbar_arrive(&ms->act_ready);  // actions in shared memory, h3 no longer needed
     }
   } else if (warp < 10) {
@@ -444,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     for (int t = 0; t <= T; ++t) {
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
-        mbar_wait(&ms->acc_v, p_acc);
+        wait_bar<PROF>(&ms->acc_v, p_acc, pc[7]);
         p_acc ^= 1u;
         fence_after_sync();
         if (l == 0) nv = (*reinterpret_cast<volatile int*>(&ms->nflag) > 0) ? 2 * kNE : kNE;
@@ -456,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
             uint32_t r[32];
             tmem_ld32(tq + (uint32_t)(m * nv + hf * 32), r);
             tmem_ld_wait();
+            if (dbg & 8) continue;
             if (l < 2) {
               const uint32_t kb_off = (uint32_t)(m * 4 + q) * 4096u;
 #pragma unroll
@@ -509,12 +547,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     for (int t = 0; t < T; ++t) {
       // ---- 1. Philox draws of this step for my 8 environments (same streams / order as env_finish_kernel) ----
       float eps[8][4], eps_r[8], uu[8];
-      if (!p.env_noise) {
+      const long long t_n0 = PROF ? clock64() : 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        eps_r[i] = 0.f;
+        uu[i] = 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eps[i][k] = 0.f;
+      }
+      if (dbg & 1) {  // ablation: no Philox draws
+      } else if (!p.env_noise) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int e = ew * 8 + i;
-          eps_r[i] = 0.f;
-          uu[i] = 1.f;
           if (e < nE) {
             curandStatePhilox4_32_10_t st;
             curand_init(p.seed_e, (unsigned long long)(e0 + e) * 32ull + lane, (c_e + (uint64_t)t) * 64ull, &st);
@@ -527,12 +572,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           }
         }
       }
+      if constexpr (PROF) pc[11] += clock64() - t_n0;
       // ---- 2. env pre-activation out of TMEM: thread c = obs column, 32 environment columns ----
-      mbar_wait(&ms->acc_env, p_env);
+      wait_bar<PROF>(&ms->acc_env, p_env, pc[8]);
       p_env ^= 1u;
-      mbar_wait(&ms->act_ready, p_act);
+      wait_bar<PROF>(&ms->act_ready, p_act, pc[9]);
       p_act ^= 1u;
-      mbar_wait(&ms->vhead, p_vh);  // the value head of this step has consumed flag / rew of the previous step
+      wait_bar<PROF>(&ms->vhead, p_vh, pc[10]);  // the value head of this step has consumed flag / rew of the previous step
       p_vh ^= 1u;
       fence_after_sync();
       {
@@ -547,33 +593,56 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
       }
       fence_before_sync();
       named_sync(3, 128);
-      // ---- 3. finish: one warp per environment ----
+      const long long t_f0 = PROF ? clock64() : 0;
+      // ---- 3. finish: warp ew owns environments ew*8 .. ew*8+7.  Written as array stages over the 8 environments
+      //      (all loads, then the math, then all stores) so that one warp has 8-32 independent chains in flight: the
+      //      per-environment loop of the first version ran at ~7k cycles per environment (one warp per scheduler, every
+      //      latency exposed).  eps[][] is reused for pre-activation -> new state.
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nk) {
+          const int c = lane + 32 * k;
+          float wa[kMaxActTc];
+#pragma unroll
+          for (int a = 0; a < kMaxActTc; ++a) wa[a] = a < act ? __ldg(p.w_a + a * obs + c) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = ew * 8 + i;
+            const float4 a0 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc);
+            const float4 a1 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc + 4);
+            float z = zs[e * obs + c];
+            z = fmaf(a0.x, wa[0], z); z = fmaf(a0.y, wa[1], z); z = fmaf(a0.z, wa[2], z); z = fmaf(a0.w, wa[3], z);
+            z = fmaf(a1.x, wa[4], z); z = fmaf(a1.y, wa[5], z); z = fmaf(a1.z, wa[6], z); z = fmaf(a1.w, wa[7], z);
+            float ep = eps[i][k];
+            if (p.env_noise && e < nE) ep = p.env_noise[((size_t)t * B + e0 + e) * (2 * obs + 2) + c];
+            eps[i][k] = tanhf(z + p.noise_std * ep);
+          }
+        }
+      }
+      float sq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float q2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nk) q2 += eps[i][k] * eps[i][k];
+        sq[i] = q2;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+      }
+      bool reset[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int e = ew * 8 + i;
-        if (e >= nE) continue;
         const int64_t row = e0 + e;
-        const float* nz = p.env_noise ? p.env_noise + ((size_t)t * B + row) * (2 * obs + 2) : nullptr;
-        float sv[4];
-        float sq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sv[k] = 0.f;
-          if (k < nk) {
-            const int c = lane + 32 * k;
-            float z = zs[e * obs + c];
-            for (int a = 0; a < act; ++a) z = fmaf(ms->act[e * kMaxActTc + a], __ldg(p.w_a + a * obs + c), z);
-            const float ep = nz ? nz[c] : eps[i][k];
-            const float s = tanhf(z + p.noise_std * ep);
-            sv[k] = s;
-            sq += s * s;
-          }
-        }
-        sq = rb::warp_sum(sq);
-        float er = 0.f, u = 1.f;
-        if (lane == 0) {
-          er = nz ? nz[obs] : eps_r[i];
-          u = nz ? nz[obs + 1] : uu[i];
+        float er = eps_r[i], u = uu[i];
+        if (p.env_noise && e < nE && lane == 0) {
+          const float* nz = p.env_noise + ((size_t)t * B + row) * (2 * obs + 2);
+          er = nz[obs];
+          u = nz[obs + 1];
         }
         er = __shfl_sync(0xffffffffu, er, 0);
         u = __shfl_sync(0xffffffffu, u, 0);
@@ -581,44 +650,69 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         const bool term = u < p.p_term;
         const bool trunc = p.max_episode_steps > 0 && el >= p.max_episode_steps;
         const bool done = term || trunc;
-        const bool reset = done && p.auto_reset;
+        reset[i] = done && p.auto_reset;
         const bool flagged = boot && (p.bootstrap_on_done ? done : trunc);
-        __syncwarp();
-        if (lane == 0) {
-          const float rw = -sq / (float)obs + p.reward_noise_std * er;
-          const size_t o = (size_t)(t + 1) * B + row;
-          p.term[o] = term;
-          p.trunc[o] = trunc;
-          p.done[o] = done;
-          ms->el[e] = reset ? 0 : el;
-          ms->flag[e] = flagged ? 1 : 0;
-          ms->rew[e] = rw;
-          if (!flagged) p.rewards[(size_t)t * B + row] = rw;  // flagged: written by the value warps with the bootstrap
+        eps_r[i] = -sq[i] / (float)obs + p.reward_noise_std * er;  // reward
+        uu[i] = __int_as_float((term ? 1 : 0) | (trunc ? 2 : 0) | (done ? 4 : 0) | (flagged ? 8 : 0) | ((reset[i] ? 0 : el) << 4));
+      }
+      __syncwarp();  // every lane has read ms->el / ms->act before lane 0 rewrites the per-environment slots
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = ew * 8 + i;
+          if (e < nE) {
+            const int64_t row = e0 + e;
+            const int bits = __float_as_int(uu[i]);
+            const size_t o = (size_t)(t + 1) * B + row;
+            p.term[o] = bits & 1;
+            p.trunc[o] = (bits >> 1) & 1;
+            p.done[o] = (bits >> 2) & 1;
+            ms->el[e] = bits >> 4;
+            ms->flag[e] = (bits >> 3) & 1;
+            ms->rew[e] = eps_r[i];
+            if (!(bits & 8)) p.rewards[(size_t)t * B + row] = eps_r[i];  // flagged: written by the value warps with the bootstrap
+          }
         }
-        curandStatePhilox4_32_10_t st;
-        if (reset && !nz) {  // replay this lane's stream up to the reset draws (rare: one env-step in ~80)
-          curand_init(p.seed_e, (unsigned long long)row * 32ull + lane, (c_e + (uint64_t)t) * 64ull, &st);
-          for (int k = 0; k < nk; ++k) (void)curand_normal(&st);
-          if (lane == 0) {
-            (void)curand_normal(&st);
-            (void)curand_uniform(&st);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = ew * 8 + i;
+        if (e >= nE) continue;
+        const int64_t row = e0 + e;
+        float nw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nw[k] = eps[i][k];
+        if (reset[i]) {  // warp-uniform, rare (one env-step in ~80): fresh state from the same stream, same draw order
+          if (p.env_noise) {
+            const float* nz = p.env_noise + ((size_t)t * B + row) * (2 * obs + 2);
+            for (int k = 0; k < nk; ++k) nw[k] = nz[obs + 2 + lane + 32 * k];
+          } else {
+            curandStatePhilox4_32_10_t st;
+            curand_init(p.seed_e, (unsigned long long)row * 32ull + lane, (c_e + (uint64_t)t) * 64ull, &st);
+            for (int k = 0; k < nk; ++k) (void)curand_normal(&st);
+            if (lane == 0) {
+              (void)curand_normal(&st);
+              (void)curand_uniform(&st);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nk) nw[k] = curand_normal(&st);
           }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < nk) {
             const int c = lane + 32 * k;
-            float s = sv[k];
-            if (t == T - 1) p.final_obs[(size_t)row * obs + c] = s;
-            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(kNE + e, lane), s);  // pre-reset observation
-            if (reset) s = nz ? nz[obs + 2 + c] : curand_normal(&st);
-            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(e, lane), s);
-            p.states[((size_t)(t + 1) * B + row) * obs + c] = s;
+            if (t == T - 1) p.final_obs[(size_t)row * obs + c] = eps[i][k];
+            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(kNE + e, lane), eps[i][k]);  // pre-reset observation
+            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(e, lane), nw[k]);
+            p.states[((size_t)(t + 1) * B + row) * obs + c] = nw[k];
           }
         }
       }
       rb::tma::fence_proxy_async();
       named_sync(3, 128);
+      if constexpr (PROF) pc[12] += clock64() - t_f0;
       if (gt == 0) {
         int n = 0;
         for (int e = 0; e < kNE; ++e) n += ms->flag[e];
@@ -630,6 +724,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     if (gt < nE) p.elapsed[e0 + gt] = ms->el[gt];  // written by this group, ordered by the last named barrier
   }
 
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && p.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 10)) {
+      for (int i = 0; i < 15; ++i)
+        if (pc[i]) p.prof[i] = pc[i];
+      if (warp == 0) p.prof[15] = clock64() - t_start;
+    }
+  }
   fence_before_sync();
   __syncthreads();
   if (warp == 1) {
@@ -662,8 +763,8 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     else if (stage < sg.a2) { seg = 3; rel = stage - sg.v1; }
     else if (stage < sg.v2) { seg = 4; rel = stage - sg.a2; }
     else { seg = 5; rel = stage - sg.v2; }
-    const int nkb = (seg < 2) ? sg.nkb0 : 8;
-    const int m = rel / nkb, kb = rel - m * nkb;
+    const int ntile = seg < 0 ? 1 : 2;  // stream order inside a layer: k-block outer, M tile inner (the MMA issue order)
+    const int kb = rel / ntile, m = rel - kb * ntile;
     const int in_dim = (seg < 2) ? a.obs : kH;
     float v[8];
 #pragma unroll
@@ -691,6 +792,18 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
 }
 
 }  // namespace
+
+static int g_tc_dbg = 0;
+static long long* g_tc_prof = nullptr;
+
+// Probe hook (tools/rollout_tc_probe.py): ablation switches (1 = no Philox draws, 2 = no MMAs, 4 = no weight loads,
+// 8 = epilogues only read the accumulators) and a device buffer of 16 int64 receiving CTA 0's wait-cycle counters
+// (selects the instrumented instantiation).  flags = 0, prof = NULL restores the production kernel.
+extern "C" int rb200_rollout_tc_debug(int flags, void* prof16) {
+  g_tc_dbg = flags;
+  g_tc_prof = static_cast<long long*>(prof16);
+  return RB200_OK;
+}
 
 extern "C" int rb200_rollout_tc_supported(const rb200_mlp_layout* L, int B) {
   if (!L) return RB200_E_NULL;
@@ -744,13 +857,16 @@ extern "C" int rb200_rollout_tc(const rb200_mlp_layout* L, const float* params, 
   a.act = L->act_dim; a.max_episode_steps = max_episode_steps; a.auto_reset = auto_reset;
   a.bootstrap_on_done = bootstrap_on_done; a.gamma = (float)gamma; a.p_term = (float)p_term;
   a.noise_std = (float)noise_std; a.reward_noise_std = (float)reward_noise_std;
+  a.dbg = g_tc_dbg; a.prof = g_tc_prof;
   static bool attr_done = false;
   if (!attr_done) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   const int grid = (B + kNE - 1) / kNE;
-  rollout_tc_kernel<<<grid, kThreads, kSmemBytes, rb::as_stream(stream)>>>(a);
+  if (g_tc_prof) rollout_tc_kernel<true><<<grid, kThreads, kSmemBytes, rb::as_stream(stream)>>>(a);
+  else rollout_tc_kernel<false><<<grid, kThreads, kSmemBytes, rb::as_stream(stream)>>>(a);
   rb::count_launch();
   RB_RETURN_LAUNCH();
 }

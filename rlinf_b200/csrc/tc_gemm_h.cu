@@ -147,6 +147,18 @@ __device__ __forceinline__ void split_tile(const uint8_t* __restrict__ src, uint
   }
 }
 
+// PROF instantiations (tools/gemm_role_probe.py): cycles each role of CTA 0 spends waiting / working
+template <bool PROF>
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long& acc) {
+  if constexpr (PROF) {
+    const long long t0 = clock64();
+    tma::mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    tma::mbar_wait(bar, parity);
+  }
+}
+
 struct __align__(16) Barriers {
   uint64_t full[kStages];
   uint64_t xf[kStages];
@@ -175,9 +187,13 @@ struct GemmParams {
   int b_mn;  // 0: weights K-major (forward), 1: MN-major (dgrad: B(n = in, k = out) = W[out][in])
   int ngroups;
   int flags;
+  long long* prof;  // [16] (PROF instantiation only)
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_constant__ GemmParams P) {
+  long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = PROF ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* staging = smem + kStages * kStageBytes;
@@ -224,7 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
       tma::prefetch_desc(&P.bl[grp]);
       const int64_t my_tiles = n_tiles > cta ? (n_tiles - cta + n_cta - 1) / n_cta : 0;
       const int64_t total = my_tiles * n_kb;
-      const int pf = 3;
+      // L2 prefetch distance in k-blocks (debug flag bits 8-15 override: 255 = off)
+      int pf = (P.flags >> 8) & 0xff;
+      pf = pf == 0 ? 3 : (pf == 255 ? 0 : pf);
       for (int64_t j = 0; j < pf && j < total; ++j)
         tma::prefetch_2d(&P.a[grp], (int)(j % n_kb) * BK, (int)((cta + (j / n_kb) * n_cta) * BM));
       for (int64_t j = 0; j < total; ++j) {
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
         if (jp < total) tma::prefetch_2d(&P.a[grp], (int)(jp % n_kb) * BK, (int)((cta + (jp / n_kb) * n_cta) * BM));
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
-        tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+        wait_bar<PROF>(&bars->empty[s], ph ^ 1u, pc[0]);
         uint8_t* st = smem + s * kStageBytes;
         uint8_t* sb = st + kA32 + 2 * kA16;
         tma::mbar_arrive_expect_tx(&bars->full[s], kA32 + 2 * kB16);
@@ -260,14 +278,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
       for (int64_t tile = cta; tile < n_tiles; tile += n_cta, ++tcount) {
         const uint32_t buf = tcount & 1u;
         const uint32_t bph = (tcount >> 1) & 1u;
-        tma::mbar_wait(&bars->tmem_empty[buf], bph ^ 1u);
+        wait_bar<PROF>(&bars->tmem_empty[buf], bph ^ 1u, pc[1]);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
-          tma::mbar_wait(&bars->full[s], ph);
-          tma::mbar_wait(&bars->xf[s], ph);
+          wait_bar<PROF>(&bars->full[s], ph, pc[2]);
+          wait_bar<PROF>(&bars->xf[s], ph, pc[3]);
           fence_after_sync();
           const uint32_t sa32 = tma::smem_u32(smem + s * kStageBytes);
           const uint64_t a_hi = desc_k_sw64(sa32 + kA32), a_lo = desc_k_sw64(sa32 + kA32 + kA16);
@@ -296,12 +314,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
       for (int kb = 0; kb < n_kb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
-        tma::mbar_wait(&bars->full[s], ph);
+        wait_bar<PROF>(&bars->full[s], ph, pc[4]);
+        const long long t_w0 = PROF ? clock64() : 0;
         uint8_t* st = smem + s * kStageBytes;
         split_tile<32 * kXfWarps>(st, st + kA32, st + kA32 + kA16, BM, t, a_scale);
         tma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+        if constexpr (PROF) pc[5] += clock64() - t_w0;
       }
     }
   } else {
@@ -325,7 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
     for (int64_t tile = cta; tile < n_tiles; tile += n_cta, ++tcount) {
       const uint32_t buf = tcount & 1u;
       const uint32_t bph = (tcount >> 1) & 1u;
-      tma::mbar_wait(&bars->tmem_full[buf], bph);
+      wait_bar<PROF>(&bars->tmem_full[buf], bph, pc[6]);
+      const long long t_e0 = PROF ? clock64() : 0;
       fence_after_sync();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
       const int64_t row0 = tile * BM + q * 32;
@@ -382,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
       fence_before_sync();
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(&bars->tmem_empty[buf]);
+      if constexpr (PROF) pc[7] += clock64() - t_e0;
     }
     if (G.amax_out != nullptr && P.epi == rb::tc::EPI_TANHGRAD) {
 #pragma unroll
@@ -391,6 +413,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
     if (lane == 0) tma::store_wait_all();
   }
 
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && P.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 2 + kXfWarps)) {
+      for (int i = 0; i < 8; ++i)
+        if (pc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(P.prof + i), (unsigned long long)pc[i]);
+      if (warp == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.prof + 8), (unsigned long long)(clock64() - t_start));
+    }
+  }
   fence_before_sync();
   __syncthreads();
   if (G.colsum != nullptr && P.epi == rb::tc::EPI_TANHGRAD)
@@ -426,7 +455,7 @@ struct WgradParams {
   float* dW[2];
   const float* amax_z[2];  // max|dZ| per group (or NULL)
   int64_t n;
-  int IN, kb_per_chunk, ngroups;
+  int IN, kb_per_chunk, ngroups, flags;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_constant__ WgradParams P) {
@@ -469,7 +498,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
   if (n_kb > 0) {
     if (warp == 0) {
       const int n_box = 4 + gB;
-      const int pf = 3;
+      int pf = (P.flags >> 8) & 0xff;
+      pf = pf == 0 ? 3 : (pf == 255 ? 0 : pf);
       if (lane < n_box)
         for (int j = 0; j < pf && j < n_kb; ++j) {
           if (lane < 4) tma::prefetch_2d(&P.z[grp], out_tile * 128 + lane * 32, (kb0 + j) * BK);
@@ -593,11 +623,13 @@ int encode_f32_sw128(CUtensorMap* out, const float* base, uint64_t rows, uint64_
 int encode_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
                int swizzle_bytes);
 
+static long long* g_prof = nullptr;  // rb200_tc_h_debug
+
 int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn, cudaStream_t st) {
   if (ngroups < 1 || ngroups > 2 || K % BK != 0 || K <= 0 || M <= 0) return RB200_E_SHAPE;
   if (b_mn && K != BN) return RB200_E_SHAPE;  // dgrad of the square hidden layers
   GemmParams P{};
-  P.M = M; P.K = K; P.epi = epi; P.b_mn = b_mn; P.ngroups = ngroups; P.flags = 0;
+  P.M = M; P.K = K; P.epi = epi; P.b_mn = b_mn; P.ngroups = ngroups; P.flags = rb::tc::g_debug_flags;
   for (int g = 0; g < ngroups; ++g) {
     const GemmLaunch& l = L[g];
     const uintptr_t al = reinterpret_cast<uintptr_t>(l.a) | reinterpret_cast<uintptr_t>(l.b_hi) |
@@ -620,16 +652,20 @@ int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn
   constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
   static_assert(kSmem <= 232448, "tc_h_gemm_kernel shared memory");
   if (!attr_done) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_h_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
     attr_done = true;
   }
+  P.prof = g_prof;
   const int64_t n_tiles = (M + BM - 1) / BM;
   const int sms = rb::sm_count();
   int per_group = sms / ngroups;
   if (per_group > n_tiles) per_group = (int)n_tiles;
   if (per_group < 1) per_group = 1;
-  tc_h_gemm_kernel<<<per_group * ngroups, kThreads, kSmem, st>>>(P);
+  if (g_prof) tc_h_gemm_kernel<true><<<per_group * ngroups, kThreads, kSmem, st>>>(P);
+  else tc_h_gemm_kernel<false><<<per_group * ngroups, kThreads, kSmem, st>>>(P);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
@@ -638,7 +674,7 @@ int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn
 int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st) {
   if (ngroups < 1 || ngroups > 2 || n <= 0 || IN <= 0 || IN > 256 || IN % 32 != 0) return RB200_E_SHAPE;
   WgradParams P{};
-  P.n = n; P.IN = IN; P.ngroups = ngroups;
+  P.n = n; P.IN = IN; P.ngroups = ngroups; P.flags = rb::tc::g_debug_flags;
   for (int g = 0; g < ngroups; ++g) {
     const uintptr_t al = reinterpret_cast<uintptr_t>(L[g].z) | reinterpret_cast<uintptr_t>(L[g].h) |
                          reinterpret_cast<uintptr_t>(L[g].dW);
@@ -689,6 +725,14 @@ int split_weights(const SplitSpec* specs, int count, cudaStream_t st) {
 
 }  // namespace tch
 }  // namespace rb
+
+// probe hook (tools/gemm_role_probe.py): 16 int64 receiving CTA 0's per-role wait / work cycles (forward / dgrad kernel:
+// 0 producer-wait-empty, 1 mma-wait-tmem_empty, 2 mma-wait-full, 3 mma-wait-xf, 4 xf-wait-full, 5 xf-work,
+// 6 epilogue-wait-tmem_full, 7 epilogue-work, 8 total); NULL restores the production kernels
+extern "C" int rb200_tc_h_debug(void* prof16) {
+  rb::tch::g_prof = static_cast<long long*>(prof16);
+  return RB200_OK;
+}
 
 // ---- unit-test entries (tests/test_gpu_tc_gemm.py) --------------------------------------------------------------------
 // C[M,256] = A[M,K] . B[256,K]^T (mode 0, forward) or A[M,256] . B[256,256] (mode 1, dgrad form: B is [out=K, in=N]);
