@@ -62,14 +62,16 @@ struct Misc {
   float mean[kNE * kMaxActTc];
   float act[kNE * kMaxActTc];
   float rew[kNE];
+  float er[kNE], uu[kNE];  // reward noise / termination uniform of this step (env warps -> finishing warps)
   int flag[kNE];
   int el[kNE];
   int nflag;
   uint32_t tmem_base;
   uint64_t full[kStages], empty[kStages];
-  uint64_t acc_a, acc_v, acc_env, opnd_a, opnd_v, act_ready, vhead, obs_ready;
+  uint64_t acc_a, acc_v, acc_env, opnd_a, opnd_v, vhead, obs_ready;
 };
-constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;
+constexpr int kArgsBytes = 512;  // shared-memory copy of the kernel arguments for the out-of-line helpers
+constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + kArgsBytes + 1024;
 static_assert(kSmemBytes <= 232448, "rollout_tc shared memory");
 
 struct TcArgs {
@@ -99,6 +101,7 @@ struct TcArgs {
   int dbg;               // ablation switches for tools/rollout_tc_probe.py (0 in production), see rb200_rollout_tc_debug
   long long* prof;       // [16] wait-cycle counters of CTA 0 (PROF instantiation only)
 };
+static_assert(sizeof(TcArgs) <= kArgsBytes, "TcArgs shared-memory copy");
 
 // ---- PTX wrappers (same instructions as tc_gemm_h.cu) ---------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -150,10 +153,6 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// K-major SWIZZLE_64B operand tile: rows of 32 fp16 (64 B), 8-row groups 512 B apart (tc_gemm_h.cu: desc_k_sw64)
-__device__ __forceinline__ uint64_t desc_k_sw64(uint32_t addr) {
-  return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -200,6 +199,210 @@ __host__ __device__ inline Segs make_segs(int obs) {
   return s;
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// Layer epilogue of one tower, ONE out-of-line copy shared by the actor and the value warps (they run it at the same
+// time: shared instruction-cache lines): thread = hidden unit j = m*128 + q*32 + lane of both M tiles, `ncol`
+// environment columns per tile read from TMEM 8 at a time; out = tanh(acc * 2^-10 + bias) written either as the next
+// layer's operand (fp16 hi | lo, K-major SWIZZLE_64B tiles of `rows` environment rows, k-block = j / 32, k = lane) or,
+// for the last layer, as fp32 [env][256] for the heads.
+__device__ __noinline__ void tower_epilogue(uint32_t tq, int ncol, uint8_t* buf, uint32_t half_bytes, uint32_t kb_bytes,
+                                            int q, int lane, float b0, float b1, int last, int skip_math) {
+  const float out_scale = 1.0f / (float)(1 << kWScaleLog2);
+  // byte offset of (row r, k = lane) inside a k-block tile: r*64 + (((lane>>3) ^ ((r>>1)&3)) << 4) + (lane&7)*2; for
+  // r = 8*g + j the swizzle term depends on j only
+  uint32_t xl[4];
+#pragma unroll
+  for (int sft = 0; sft < 4; ++sft) xl[sft] = (uint32_t)((((lane >> 3) ^ sft) << 4) + (lane & 7) * 2);
+  float* f32 = reinterpret_cast<float*>(buf);
+#pragma unroll 1
+  for (int m = 0; m < 2; ++m) {
+    const float b = m ? b1 : b0;
+    const uint32_t kb_off = (uint32_t)(m * 4 + q) * kb_bytes;
+    const int j = m * 128 + q * 32 + lane;
+#pragma unroll 1
+    for (int g = 0; g < ncol / 8; ++g) {
+      uint32_t r[8];
+      tmem_ld8(tq + (uint32_t)(m * ncol + g * 8), r);
+      tmem_ld_wait();
+      if (skip_math) continue;
+      if (!last) {
+        const uint32_t base = kb_off + (uint32_t)g * 512u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          store_split(buf, half_bytes, base + (uint32_t)i * 64u + xl[(i >> 1) & 3], tanh_fast(__uint_as_float(r[i]) * out_scale + b));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f32[(g * 8 + i) * kH + j] = tanh_fast(__uint_as_float(r[i]) * out_scale + b);
+      }
+    }
+  }
+}
+
+// ---- Philox draws as out-of-line functions: inlined at every use (8 + 8 + 1 sites, ~700 instructions each) the kernel
+//      was 230 KB of SASS executed by 16 warps at different program counters - far beyond the instruction caches ----
+struct EnvDraws {
+  float e[4];  // state noise of observation columns lane, lane+32, lane+64, lane+96
+  float er, u; // reward noise and termination uniform (lane 0's stream only)
+};
+// the draws of env_finish_kernel (rollout.cu) for one (environment row, lane) stream of one step, in its order
+__device__ __noinline__ EnvDraws env_draws(unsigned long long seed, unsigned long long subseq, unsigned long long offset,
+                                           int nk, int lane0) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, subseq, offset, &st);
+  EnvDraws d;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d.e[k] = (k < nk) ? curand_normal(&st) : 0.f;
+  d.er = 0.f;
+  d.u = 1.f;
+  if (lane0) {
+    d.er = curand_normal(&st);
+    d.u = curand_uniform(&st);
+  }
+  return d;
+}
+// the N(0,1) reset state that FOLLOWS those draws in the same stream
+__device__ __noinline__ EnvDraws env_reset_draws(unsigned long long seed, unsigned long long subseq,
+                                                 unsigned long long offset, int nk, int lane0) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, subseq, offset, &st);
+  for (int k = 0; k < nk; ++k) (void)curand_normal(&st);
+  if (lane0) {
+    (void)curand_normal(&st);
+    (void)curand_uniform(&st);
+  }
+  EnvDraws d;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d.e[k] = (k < nk) ? curand_normal(&st) : 0.f;
+  d.er = 0.f;
+  d.u = 1.f;
+  return d;
+}
+__device__ __noinline__ float policy_draw(unsigned long long seed, unsigned long long subseq, unsigned long long offset) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, subseq, offset, &st);
+  return curand_normal(&st);
+}
+
+// Dynamics finish of 4 environments [w8*4, w8*4+4) by one warp (8 warps share a step: the actor group is idle once the
+// actions are sampled, so it takes half of the environments).  Array stages over the 4 environments - all loads, then
+// the math, then all stores - keep 4-16 independent chains in flight per lane.  zs = x.W_s out of TMEM, eps_s = this
+// step's N(0,1) draws, both fp32 [32][obs] in the (now free) actor buffer.  Same arithmetic order as env_finish_kernel
+// (rollout.cu) except tanh (MUFU-based tanh_fast, 3e-7 abs).
+__device__ __noinline__ void env_finish4(const TcArgs& p, Misc* ms, uint8_t* obuf, uint32_t ob_half, const float* zs,
+                                            const float* eps_s, int w8, int lane, int t, int e0, int nE, int nk,
+                                            uint64_t c_e, bool boot) {
+  const int obs = p.obs, B = p.B, T = p.T;
+  float v[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i][k] = 0.f;
+    if (k < nk) {
+      const int c = lane + 32 * k;
+      float wa[kMaxActTc];
+#pragma unroll
+      for (int a = 0; a < kMaxActTc; ++a) wa[a] = a < p.act ? __ldg(p.w_a + a * obs + c) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = w8 * 4 + i;
+        const float4 a0 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc);
+        const float4 a1 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc + 4);
+        float z = zs[e * obs + c];
+        z = fmaf(a0.x, wa[0], z); z = fmaf(a0.y, wa[1], z); z = fmaf(a0.z, wa[2], z); z = fmaf(a0.w, wa[3], z);
+        z = fmaf(a1.x, wa[4], z); z = fmaf(a1.y, wa[5], z); z = fmaf(a1.z, wa[6], z); z = fmaf(a1.w, wa[7], z);
+        float ep = eps_s[e * obs + c];
+        if (p.env_noise && e < nE) ep = p.env_noise[((size_t)t * B + e0 + e) * (2 * obs + 2) + c];
+        v[i][k] = tanh_fast(z + p.noise_std * ep);
+      }
+    }
+  }
+  float sq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sq[i] = (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+  }
+  bool reset[4];
+  float rw[4];
+  int bits[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = w8 * 4 + i;
+    float er = ms->er[e], u = ms->uu[e];
+    if (p.env_noise && e < nE) {
+      const float* nz = p.env_noise + ((size_t)t * B + e0 + e) * (2 * obs + 2);
+      er = nz[obs];
+      u = nz[obs + 1];
+    }
+    const int el = ms->el[e] + 1;
+    const bool term = u < p.p_term;
+    const bool trunc = p.max_episode_steps > 0 && el >= p.max_episode_steps;
+    const bool done = term || trunc;
+    reset[i] = done && p.auto_reset;
+    const bool flagged = boot && (p.bootstrap_on_done ? done : trunc);
+    rw[i] = -sq[i] / (float)obs + p.reward_noise_std * er;
+    bits[i] = (term ? 1 : 0) | (trunc ? 2 : 0) | (done ? 4 : 0) | (flagged ? 8 : 0) | ((reset[i] ? 0 : el) << 4);
+  }
+  __syncwarp();  // every lane has read ms->el before lane 0 rewrites the per-environment slots
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = w8 * 4 + i;
+      if (e < nE) {
+        const int64_t row = e0 + e;
+        const size_t o = (size_t)(t + 1) * B + row;
+        p.term[o] = bits[i] & 1;
+        p.trunc[o] = (bits[i] >> 1) & 1;
+        p.done[o] = (bits[i] >> 2) & 1;
+        ms->el[e] = bits[i] >> 4;
+        ms->flag[e] = (bits[i] >> 3) & 1;
+        ms->rew[e] = rw[i];
+        if (!(bits[i] & 8)) p.rewards[(size_t)t * B + row] = rw[i];  // flagged: written by the value warps with the bootstrap
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = w8 * 4 + i;
+    if (e >= nE) continue;
+    const int64_t row = e0 + e;
+    float nw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nw[k] = v[i][k];
+    if (reset[i]) {  // warp-uniform, rare (one env-step in ~80): fresh state from the same stream, same draw order
+      if (p.env_noise) {
+        const float* nz = p.env_noise + ((size_t)t * B + row) * (2 * obs + 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nk) nw[k] = nz[obs + 2 + lane + 32 * k];
+      } else {
+        const EnvDraws d = env_reset_draws(p.seed_e, (unsigned long long)row * 32ull + lane, (c_e + (uint64_t)t) * 64ull,
+                                           nk, lane == 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nw[k] = d.e[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nk) {
+        const int c = lane + 32 * k;
+        if (t == T - 1) p.final_obs[(size_t)row * obs + c] = v[i][k];
+        store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(kNE + e, lane), v[i][k]);  // pre-reset observation
+        store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(e, lane), nw[k]);
+        p.states[((size_t)(t + 1) * B + row) * obs + c] = nw[k];
+      }
+    }
+  }
+}
+
 // wait on an mbarrier; the PROF instantiation accumulates the cycles spent waiting (tools/rollout_tc_probe.py)
 template <bool PROF>
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long& acc) {
@@ -221,6 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
   uint8_t* abuf = smem + kOffAbuf;
   uint8_t* vbuf = smem + kOffVbuf;
   Misc* ms = reinterpret_cast<Misc*>(smem + kOffMisc);
+  // out-of-line helpers read the arguments from shared memory (a reference to the kernel parameter would be copied to
+  // the local-memory stack of every thread)
+  TcArgs* pa = reinterpret_cast<TcArgs*>(smem + kOffMisc + ((sizeof(Misc) + 15) & ~size_t(15)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int obs = p.obs, act = p.act, T = p.T, B = p.B;
@@ -235,6 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
   const bool boot = p.auto_reset != 0;  // the value head exists (rb200_rollout_tc_supported)
 
   // ---- setup ----
+  for (int i = tid; i < (int)(sizeof(TcArgs) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(pa)[i] = reinterpret_cast<const uint32_t*>(&p)[i];
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&ms->full[s], 1);
@@ -245,7 +453,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     mbar_init(&ms->acc_env, 1);
     mbar_init(&ms->opnd_a, 4);
     mbar_init(&ms->opnd_v, 4);
-    mbar_init(&ms->act_ready, 4);
     mbar_init(&ms->vhead, 4);
     mbar_init(&ms->obs_ready, 1);
     ms->nflag = 0;
@@ -282,11 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
   if (warp == 0) {
     // ================= weight-stream producer =================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       auto stream = [&](int stage0, int n) {
-        for (int i = 0; i < n; ++i, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
+        for (int i = 0; i < n; ++i, s = (s + 1 == kStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           wait_bar<PROF>(&ms->empty[s], ph ^ 1u, pc[0]);
           if (dbg & 4) {  // ablation: no weight traffic (the ring keeps whatever it holds)
             mbar_arrive(&ms->full[s]);
@@ -304,34 +509,42 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      uint32_t it = 0;
+      // The N = 32 MMAs are short (16-32 clk of tensor work): this single thread's issue rate is what bounds the
+      // tensor phase, so the loop is kept lean - ring slot / phase by counters, descriptors as {lo, hi} words with
+      // only the 14-bit address field changing (K-major SWIZZLE_64B: LBO 1, SBO 512 B, version 1, layout 4).
+      uint32_t slot = 0, ph = 0;
       const uint32_t ring_a = smem_u32(ring), obuf_a = smem_u32(obuf), abuf_a = smem_u32(abuf), vbuf_a = smem_u32(vbuf);
+      constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);  // bits 32..63 of desc_k_sw64
+      auto desc = [&](uint32_t addr) -> uint64_t {
+        return ((uint64_t)kDescHi << 32) | (uint64_t)(((addr & 0x3ffffu) >> 4) | (1u << 16));
+      };
       // one layer: D[tile m] (TMEM columns d_col + m*N) = W tile m [128 x 32*nkb] . operand[N rows x 32*nkb]^T
       auto seg = [&](int ntile, int nkb, uint32_t b_hi_addr, uint32_t b_half, uint32_t b_kb_stride, uint32_t d_col, int N) {
         const uint32_t idesc = idesc_f16(128, N);
-        // k-block outer, M tile inner: consecutive MMAs alternate between the two accumulator tiles, so the
-        // accumulate-into-the-same-tile dependency of these short (N = 32) MMAs overlaps with the other tile's
+        // k-block outer, M tile inner: consecutive MMAs alternate between the two accumulator tiles
         for (int kb = 0; kb < nkb; ++kb) {
-          for (int m = 0; m < ntile; ++m, ++it) {
+          const uint32_t sb = b_hi_addr + (uint32_t)kb * b_kb_stride;
+          const uint64_t b_hi = desc(sb), b_lo = desc(sb + b_half);
+          const uint32_t acc0 = kb > 0 ? 1u : 0u;
+          for (int m = 0; m < ntile; ++m) {
             const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(m * N);
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1u;
-            wait_bar<PROF>(&ms->full[s], ph, pc[1]);
+            wait_bar<PROF>(&ms->full[slot], ph, pc[1]);
             fence_after_sync();
-            const uint32_t sa = ring_a + s * kStageBytes;
-            const uint64_t a_hi = desc_k_sw64(sa), a_lo = desc_k_sw64(sa + kHalfTile);
-            const uint32_t sb = b_hi_addr + (uint32_t)kb * b_kb_stride;
-            const uint64_t b_hi = desc_k_sw64(sb), b_lo = desc_k_sw64(sb + b_half);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (dbg & 2) break;  // ablation: no tensor-core work
-              const uint64_t ka = (uint64_t)(2 * k);  // 16 fp16 = 32 B along the 64-B row
-              const uint32_t accf = (kb > 0 || k > 0) ? 1u : 0u;
-              mma_f16(d_tmem, a_lo + ka, b_hi + ka, idesc, accf);  // small terms first
-              mma_f16(d_tmem, a_hi + ka, b_lo + ka, idesc, 1u);
-              mma_f16(d_tmem, a_hi + ka, b_hi + ka, idesc, 1u);
+            const uint32_t sa = ring_a + slot * kStageBytes;
+            const uint64_t a_hi = desc(sa), a_lo = desc(sa + kHalfTile);
+            if (!(dbg & 2)) {  // (ablation: no tensor-core work)
+              mma_f16(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+              mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+              mma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+              mma_f16(d_tmem, a_lo + 2, b_hi + 2, idesc, 1u);  // next 16 fp16 = 32 B along the 64-B row
+              mma_f16(d_tmem, a_hi + 2, b_lo + 2, idesc, 1u);
+              mma_f16(d_tmem, a_hi + 2, b_hi + 2, idesc, 1u);
             }
-            mma_commit(&ms->empty[s]);
+            mma_commit(&ms->empty[slot]);
+            if (++slot == kStages) {
+              slot = 0;
+              ph ^= 1u;
+            }
           }
         }
       };
@@ -345,32 +558,31 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           fence_after_sync();
         }
         const int nv = (*reinterpret_cast<volatile int*>(&ms->nflag) > 0) ? 2 * kNE : kNE;
-        if (!tail) {
-          seg(1, sg.nkb0, obuf_a, ob_half, 4096u, kAccEnv, kNE);
-          mma_commit(&ms->acc_env);
-          seg(2, sg.nkb0, obuf_a, ob_half, 4096u, kAccA, kNE);
-          mma_commit(&ms->acc_a);
-        }
-        if (t > 0) {  // accumulator columns of the value tower are free once the previous value head has read them
-          wait_bar<PROF>(&ms->vhead, p_vh, pc[3]);
-          p_vh ^= 1u;
-          fence_after_sync();
-        }
-        seg(2, sg.nkb0, obuf_a, ob_half, 4096u, kAccV, nv);
-        mma_commit(&ms->acc_v);
-        for (int l = 1; l < 3; ++l) {
-          if (!tail) {
+        // segment order of the weight stream: ENV, A.L0, V.L0, A.L1, V.L1, A.L2, V.L2 (rolled: one copy of the issue code)
+#pragma unroll 1
+        for (int sgi = 0; sgi < 7; ++sgi) {
+          const bool is_v = sgi >= 2 && !(sgi & 1);
+          if (tail && !is_v) continue;
+          const int layer = sgi == 0 ? 0 : (sgi - 1) >> 1;
+          if (is_v) {
+            if (layer == 0) {
+              if (t > 0) {  // accumulator columns of the value tower are free once the previous value head has read them
+                wait_bar<PROF>(&ms->vhead, p_vh, pc[3]);
+                p_vh ^= 1u;
+              }
+            } else {
+              wait_bar<PROF>(&ms->opnd_v, p_ov, pc[5]);
+              p_ov ^= 1u;
+            }
+          } else if (layer > 0) {
             wait_bar<PROF>(&ms->opnd_a, p_oa, pc[4]);
             p_oa ^= 1u;
-            fence_after_sync();
-            seg(2, 8, abuf_a, kAbufHalf, 2048u, kAccA, kNE);
-            mma_commit(&ms->acc_a);
           }
-          wait_bar<PROF>(&ms->opnd_v, p_ov, pc[5]);
-          p_ov ^= 1u;
           fence_after_sync();
-          seg(2, 8, vbuf_a, kVbufHalf, 4096u, kAccV, nv);
-          mma_commit(&ms->acc_v);
+          seg(sgi == 0 ? 1 : 2, layer == 0 ? sg.nkb0 : 8, layer == 0 ? obuf_a : (is_v ? vbuf_a : abuf_a),
+              layer == 0 ? ob_half : (is_v ? (uint32_t)kVbufHalf : (uint32_t)kAbufHalf),
+              (layer == 0 || is_v) ? 4096u : 2048u, sgi == 0 ? kAccEnv : (is_v ? kAccV : kAccA), is_v ? nv : kNE);
+          mma_commit(sgi == 0 ? &ms->acc_env : (is_v ? &ms->acc_v : &ms->acc_a));
         }
       }
     }
@@ -393,24 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         p_acc ^= 1u;
         fence_after_sync();
         const long long t_e0 = PROF ? clock64() : 0;
-#pragma unroll 1
-        for (int m = 0; m < 2; ++m) {
-          uint32_t r[32];
-          tmem_ld32(tq + (uint32_t)(m * kNE), r);
-          tmem_ld_wait();
-          const float b = bias[l][m];
-          if (dbg & 8) continue;  // ablation: accumulator read only
-          if (l < 2) {
-            const uint32_t kb_off = (uint32_t)(m * 4 + q) * 2048u;  // hidden unit j = m*128 + q*32 + lane -> k-block j/32
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              store_split(abuf, kAbufHalf, kb_off + sw64_off(e, lane), tanh_fast(__uint_as_float(r[e]) * out_scale + b));
-          } else {
-            const int j = m * 128 + q * 32 + lane;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) h3[e * kH + j] = tanh_fast(__uint_as_float(r[e]) * out_scale + b);
-          }
-        }
+        tower_epilogue(tq, kNE, abuf, kAbufHalf, 2048u, q, lane, bias[l][0], bias[l][1], l == 2, dbg & 8);
         fence_before_sync();
         if (l < 2) {
           rb::tma::fence_proxy_async();
@@ -448,9 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           if (p.policy_noise) {
             z = p.policy_noise[((size_t)t * B + row) * act + a];
           } else {
-            curandStatePhilox4_32_10_t st;
-            curand_init(p.seed_p, (unsigned long long)(row * act + a), p.offset_p + 4ull * (c_p + (uint64_t)t), &st);
-            z = curand_normal(&st);
+            z = policy_draw(p.seed_p, (unsigned long long)(row * act + a), p.offset_p + 4ull * (c_p + (uint64_t)t));
           }
           const float xa = mean + sd * z;
           const float d = xa - mean;
@@ -461,9 +654,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           ms->act[e * kMaxActTc + a] = xa;
         }
       }
-      __syncwarp();
       if constexpr (PROF) pc[14] += clock64() - t_h0;
-      if (lane == 0) mbar_arrive(&ms->act_ready);  // actions in shared memory, h3 no longer needed
+      // ---- env finish, shared with the env warps (barrier 4 = actor + env groups): #1 actions sampled / h3 dead,
+      //      #2 zs + eps in the actor buffer, #3 next observation operand complete ----
+      named_sync(4, 256);
+      named_sync(4, 256);
+      env_finish4(*pa, ms, obuf, (uint32_t)sg.nkb0 * 4096u, reinterpret_cast<const float*>(abuf),
+                  reinterpret_cast<const float*>(abuf + kAbufHalf), warp - 2, lane, t, e0, nE, sg.nkb0, c_e, boot);
+      rb::tma::fence_proxy_async();
+      named_sync(4, 256);
     }
   } else if (warp < 10) {
     // ================= value tower: epilogues, value head, truncation bootstrap =================
@@ -485,29 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         p_acc ^= 1u;
         fence_after_sync();
         if (l == 0) nv = (*reinterpret_cast<volatile int*>(&ms->nflag) > 0) ? 2 * kNE : kNE;
-#pragma unroll 1
-        for (int m = 0; m < 2; ++m) {
-          const float b = bias[l][m];
-#pragma unroll 1
-          for (int hf = 0; hf < nv / 32; ++hf) {
-            uint32_t r[32];
-            tmem_ld32(tq + (uint32_t)(m * nv + hf * 32), r);
-            tmem_ld_wait();
-            if (dbg & 8) continue;
-            if (l < 2) {
-              const uint32_t kb_off = (uint32_t)(m * 4 + q) * 4096u;
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                store_split(vbuf, kVbufHalf, kb_off + sw64_off(hf * 32 + e, lane),
-                            tanh_fast(__uint_as_float(r[e]) * out_scale + b));
-            } else {
-              const int j = m * 128 + q * 32 + lane;
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                g3[(hf * 32 + e) * kH + j] = tanh_fast(__uint_as_float(r[e]) * out_scale + b);
-            }
-          }
-        }
+        tower_epilogue(tq, nv, vbuf, kVbufHalf, 4096u, q, lane, bias[l][0], bias[l][1], l == 2, dbg & 8);
         fence_before_sync();
         if (l < 2) {
           rb::tma::fence_proxy_async();
@@ -540,10 +717,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
     // ================= env warps: noise, dynamics finish, auto-reset, next observation operand =================
     const int q = warp & 3, ew = warp - 10, gt = tid - 320;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + kAccEnv;
-    float* zs = reinterpret_cast<float*>(abuf);  // [32][obs] fp32, aliases the actor buffer (free between act_ready and the next L0)
+    float* zs = reinterpret_cast<float*>(abuf);  // [32][obs] fp32, aliases the actor buffer (free between barrier #1 and the next L0)
+    float* eps_s = reinterpret_cast<float*>(abuf + kAbufHalf);  // [32][obs] fp32 draws of this step
     const int nk = sg.nkb0;                       // observation columns per lane
     const uint32_t ob_half = (uint32_t)sg.nkb0 * 4096u;
-    uint32_t p_env = 0, p_act = 0, p_vh = 0;
+    uint32_t p_env = 0, p_vh = 0;
     for (int t = 0; t < T; ++t) {
       // ---- 1. Philox draws of this step for my 8 environments (same streams / order as env_finish_kernel) ----
       float eps[8][4], eps_r[8], uu[8];
@@ -561,29 +739,41 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         for (int i = 0; i < 8; ++i) {
           const int e = ew * 8 + i;
           if (e < nE) {
-            curandStatePhilox4_32_10_t st;
-            curand_init(p.seed_e, (unsigned long long)(e0 + e) * 32ull + lane, (c_e + (uint64_t)t) * 64ull, &st);
+            const EnvDraws d = env_draws(p.seed_e, (unsigned long long)(e0 + e) * 32ull + lane,
+                                         (c_e + (uint64_t)t) * 64ull, nk, lane == 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) eps[i][k] = (k < nk) ? curand_normal(&st) : 0.f;
-            if (lane == 0) {
-              eps_r[i] = curand_normal(&st);
-              uu[i] = curand_uniform(&st);
-            }
+            for (int k = 0; k < 4; ++k) eps[i][k] = d.e[k];
+            eps_r[i] = d.er;
+            uu[i] = d.u;
           }
         }
       }
       if constexpr (PROF) pc[11] += clock64() - t_n0;
-      // ---- 2. env pre-activation out of TMEM: thread c = obs column, 32 environment columns ----
+      // ---- 2. wait for the env accumulator and the value head, meet the actor group (#1: h3 dead, actions sampled),
+      //         then park x.W_s (TMEM -> fp32 [32][obs]) and this step's draws in the free actor buffer ----
       wait_bar<PROF>(&ms->acc_env, p_env, pc[8]);
       p_env ^= 1u;
-      wait_bar<PROF>(&ms->act_ready, p_act, pc[9]);
-      p_act ^= 1u;
       wait_bar<PROF>(&ms->vhead, p_vh, pc[10]);  // the value head of this step has consumed flag / rew of the previous step
       p_vh ^= 1u;
       fence_after_sync();
+      const long long t_b0 = PROF ? clock64() : 0;
+      named_sync(4, 256);
+      if constexpr (PROF) pc[9] += clock64() - t_b0;
+      const long long t_f0 = PROF ? clock64() : 0;
       {
         uint32_t r[32];
         tmem_ld32(tq, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = ew * 8 + i;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < nk) eps_s[e * obs + lane + 32 * k] = eps[i][k];
+          if (lane == 0) {
+            ms->er[e] = eps_r[i];
+            ms->uu[e] = uu[i];
+          }
+        }
         tmem_ld_wait();
         const int c = q * 32 + lane;
         if (c < obs) {
@@ -592,126 +782,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
         }
       }
       fence_before_sync();
-      named_sync(3, 128);
-      const long long t_f0 = PROF ? clock64() : 0;
-      // ---- 3. finish: warp ew owns environments ew*8 .. ew*8+7.  Written as array stages over the 8 environments
-      //      (all loads, then the math, then all stores) so that one warp has 8-32 independent chains in flight: the
-      //      per-environment loop of the first version ran at ~7k cycles per environment (one warp per scheduler, every
-      //      latency exposed).  eps[][] is reused for pre-activation -> new state.
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < nk) {
-          const int c = lane + 32 * k;
-          float wa[kMaxActTc];
-#pragma unroll
-          for (int a = 0; a < kMaxActTc; ++a) wa[a] = a < act ? __ldg(p.w_a + a * obs + c) : 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int e = ew * 8 + i;
-            const float4 a0 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc);
-            const float4 a1 = *reinterpret_cast<const float4*>(ms->act + e * kMaxActTc + 4);
-            float z = zs[e * obs + c];
-            z = fmaf(a0.x, wa[0], z); z = fmaf(a0.y, wa[1], z); z = fmaf(a0.z, wa[2], z); z = fmaf(a0.w, wa[3], z);
-            z = fmaf(a1.x, wa[4], z); z = fmaf(a1.y, wa[5], z); z = fmaf(a1.z, wa[6], z); z = fmaf(a1.w, wa[7], z);
-            float ep = eps[i][k];
-            if (p.env_noise && e < nE) ep = p.env_noise[((size_t)t * B + e0 + e) * (2 * obs + 2) + c];
-            eps[i][k] = tanhf(z + p.noise_std * ep);
-          }
-        }
-      }
-      float sq[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float q2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < nk) q2 += eps[i][k] * eps[i][k];
-        sq[i] = q2;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
-      }
-      bool reset[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = ew * 8 + i;
-        const int64_t row = e0 + e;
-        float er = eps_r[i], u = uu[i];
-        if (p.env_noise && e < nE && lane == 0) {
-          const float* nz = p.env_noise + ((size_t)t * B + row) * (2 * obs + 2);
-          er = nz[obs];
-          u = nz[obs + 1];
-        }
-        er = __shfl_sync(0xffffffffu, er, 0);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        const int el = ms->el[e] + 1;
-        const bool term = u < p.p_term;
-        const bool trunc = p.max_episode_steps > 0 && el >= p.max_episode_steps;
-        const bool done = term || trunc;
-        reset[i] = done && p.auto_reset;
-        const bool flagged = boot && (p.bootstrap_on_done ? done : trunc);
-        eps_r[i] = -sq[i] / (float)obs + p.reward_noise_std * er;  // reward
-        uu[i] = __int_as_float((term ? 1 : 0) | (trunc ? 2 : 0) | (done ? 4 : 0) | (flagged ? 8 : 0) | ((reset[i] ? 0 : el) << 4));
-      }
-      __syncwarp();  // every lane has read ms->el / ms->act before lane 0 rewrites the per-environment slots
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int e = ew * 8 + i;
-          if (e < nE) {
-            const int64_t row = e0 + e;
-            const int bits = __float_as_int(uu[i]);
-            const size_t o = (size_t)(t + 1) * B + row;
-            p.term[o] = bits & 1;
-            p.trunc[o] = (bits >> 1) & 1;
-            p.done[o] = (bits >> 2) & 1;
-            ms->el[e] = bits >> 4;
-            ms->flag[e] = (bits >> 3) & 1;
-            ms->rew[e] = eps_r[i];
-            if (!(bits & 8)) p.rewards[(size_t)t * B + row] = eps_r[i];  // flagged: written by the value warps with the bootstrap
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = ew * 8 + i;
-        if (e >= nE) continue;
-        const int64_t row = e0 + e;
-        float nw[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nw[k] = eps[i][k];
-        if (reset[i]) {  // warp-uniform, rare (one env-step in ~80): fresh state from the same stream, same draw order
-          if (p.env_noise) {
-            const float* nz = p.env_noise + ((size_t)t * B + row) * (2 * obs + 2);
-            for (int k = 0; k < nk; ++k) nw[k] = nz[obs + 2 + lane + 32 * k];
-          } else {
-            curandStatePhilox4_32_10_t st;
-            curand_init(p.seed_e, (unsigned long long)row * 32ull + lane, (c_e + (uint64_t)t) * 64ull, &st);
-            for (int k = 0; k < nk; ++k) (void)curand_normal(&st);
-            if (lane == 0) {
-              (void)curand_normal(&st);
-              (void)curand_uniform(&st);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < nk) nw[k] = curand_normal(&st);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < nk) {
-            const int c = lane + 32 * k;
-            if (t == T - 1) p.final_obs[(size_t)row * obs + c] = eps[i][k];
-            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(kNE + e, lane), eps[i][k]);  // pre-reset observation
-            store_split(obuf, ob_half, (uint32_t)k * 4096u + sw64_off(e, lane), nw[k]);
-            p.states[((size_t)(t + 1) * B + row) * obs + c] = nw[k];
-          }
-        }
-      }
+      named_sync(4, 256);
+      // ---- 3. finish 4 environments per warp (the actor group takes environments 0..15) ----
+      env_finish4(*pa, ms, obuf, ob_half, zs, eps_s, 4 + ew, lane, t, e0, nE, nk, c_e, boot);
       rb::tma::fence_proxy_async();
-      named_sync(3, 128);
+      named_sync(4, 256);
       if constexpr (PROF) pc[12] += clock64() - t_f0;
       if (gt == 0) {
         int n = 0;

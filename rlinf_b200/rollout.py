@@ -164,6 +164,7 @@ class RolloutWorker:
     """One rank's env + policy replica."""
 
     FUSED_AUTO_MAX_ENVS_PER_CTA = 16
+    TC_AUTO_MIN_ENVS = 640
 
     def __init__(self, cfg, policy, env, buffer: RolloutBuffer):
         self.cfg, self.policy, self.env, self.buf = cfg, policy, env, buffer
@@ -190,8 +191,11 @@ class RolloutWorker:
         if mode == "tc" and not tc_ok:
             raise ValueError("rollout.fused_kernel='tc' needs hidden 256, a value head, act_dim <= 8, obs_dim % 32 == 0 "
                              "and obs_dim <= 128 (rb200_rollout_tc_supported)")
-        # tensor-core persistent kernel: one launch per rollout at any B (csrc/rollout_tc.cu) - the default when supported
-        self._tc = tc_ok and mode in ("auto", "tc")
+        # tensor-core persistent kernel (csrc/rollout_tc.cu): one launch per rollout, ~44 us per env step whatever B is
+        # (32 envs per CTA, measured 22.7 ms per 512-step rollout at B = 512 .. 4096).  The fp32 SIMT persistent kernel is
+        # faster while a CTA owns <= 4 environments (19 ms at B = 512), so "auto" picks the tensor-core kernel from
+        # TC_AUTO_MIN_ENVS environments per rank on.
+        self._tc = tc_ok and (mode == "tc" or (mode == "auto" and int(buffer.B) >= self.TC_AUTO_MIN_ENVS))
         if mode == "simt":
             mode = True
         if self._tc:

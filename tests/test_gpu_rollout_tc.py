@@ -59,7 +59,7 @@ def test_rollout_tc_vs_oracle(B, obs, act, bootstrap_type):
     assert (run.env.elapsed.cpu() == orc.env.elapsed).all()
 
 
-def test_rollout_tc_is_the_default_and_matches_per_kernel_path_on_device_rng():
+def test_rollout_tc_matches_per_kernel_path_on_device_rng():
     """Same Philox streams and draw order as the per-kernel loop: flags and elapsed counters agree exactly over three
     consecutive rollouts (auto-reset draws included), floats up to the fp32 summation order of the two GEMM paths."""
     from rlinf_b200.config import synthetic_ppo_config
@@ -67,13 +67,13 @@ def test_rollout_tc_is_the_default_and_matches_per_kernel_path_on_device_rng():
 
     B, T, obs, act = 300, 8, 32, 3
     bufs = []
-    for mode in ("auto", False):
+    for mode in ("tc", False):
         cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, **{"rollout.fused_kernel": mode,
                                                                               "env.train.p_term": 0.03,
                                                                               "env.train.max_episode_steps": 5,
                                                                               "algorithm.bootstrap_type": "always"})
         run = EmbodiedRunner(cfg)
-        assert run.rollout._tc == (mode == "auto")
+        assert run.rollout._tc == (mode == "tc")
         out = []
         for _ in range(3):
             run.rollout_phase()
@@ -88,16 +88,18 @@ def test_rollout_tc_is_the_default_and_matches_per_kernel_path_on_device_rng():
     assert bool(bufs[0][2]["dones"].any())
 
 
-def test_rollout_tc_full_length_episode_statistics():
+def test_rollout_tc_default_and_full_length_episode_statistics():
     """T = 512 at the headline network shapes on the device RNG: finite outputs, the truncation period shows up in the
     flags, and every flagged step carries its bootstrap (rewards differ from the raw reward by gamma * final value)."""
     from rlinf_b200.config import synthetic_ppo_config
     from rlinf_b200.runner import EmbodiedRunner
 
-    B, T = 512, 512
+    B, T = 1024, 512
     cfg = synthetic_ppo_config(B=B, T=T, obs_dim=128, action_dim=8)
     run = EmbodiedRunner(cfg)
-    assert run.rollout._tc
+    assert run.rollout._tc  # the default from 640 environments per rank on (RolloutWorker.TC_AUTO_MIN_ENVS)
+    small = EmbodiedRunner(synthetic_ppo_config(B=256, T=8, obs_dim=128, action_dim=8))
+    assert not small.rollout._tc and small.rollout._fused
     run.rollout_phase()
     torch.cuda.synchronize()
     b = _cpu_batch(run.buffer.as_batch())
