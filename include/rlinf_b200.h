@@ -424,6 +424,22 @@ int rb200_synth_env_step(const float* w_s, const float* w_a, const float* state,
                          int B, int obs, int act, int max_episode_steps, int auto_reset, float p_term,
                          float noise_std, float reward_noise_std, uint64_t seed,
                          const uint64_t* counter_dev, rb200_stream_t stream);
+/* env.chunk_step for num_action_chunks = C > 1 (rlinf/envs/maniskill/maniskill_env.py:327-375): C sub-steps of the
+ * synthetic env WITHOUT auto-reset (sub-step c takes columns [c*act, (c+1)*act) of chunk_actions [B, C*act]), rewards
+ * [B,C] of every sub-step, terminations / truncations / dones [B,C] all-zero except the last column = any over the
+ * chunk, ONE auto-reset after the chunk (final_obs = observation before it).  noise: optional pre-drawn
+ * [B, C*(obs+2) + obs] = per sub-step eps[obs] | eps_r | u_term, then the reset state; else Philox(seed, counter).
+ * scratch: 3*B*obs floats. */
+int rb200_synth_env_chunk_step(const float* w_s, const float* w_a, const float* state, const float* chunk_actions,
+                               const float* noise, float* next_state, float* final_obs, float* rewards,
+                               uint8_t* term, uint8_t* trunc, uint8_t* done, int32_t* elapsed, float* scratch,
+                               int B, int obs, int act, int C, int max_episode_steps, int auto_reset, float p_term,
+                               float noise_std, float reward_noise_std, uint64_t seed, const uint64_t* counter_dev,
+                               rb200_stream_t stream);
+/* strided form of rb200_bootstrap_rewards for the last sub-step of a chunk:
+ * rewards[b*ld_rewards] += gamma * final_values[b*value_dim] where flag[b*ld_flag]  (env_worker.py:736-758) */
+int rb200_bootstrap_rewards_ld(float* rewards, int ld_rewards, const float* final_values, int value_dim,
+                               const uint8_t* flag, int ld_flag, int B, double gamma, rb200_stream_t stream);
 /* rewards[b] += gamma * final_values[b*value_dim] where flag[b]  (compute_bootstrap_rewards,
  * workers/env/env_worker.py:736-758; flag = truncations ("standard") or dones ("always")). */
 int rb200_bootstrap_rewards(float* rewards, const float* final_values, const uint8_t* flag, int B,

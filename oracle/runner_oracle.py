@@ -58,8 +58,56 @@ class SyntheticEnvCPU:
             self.elapsed[done] = 0
         return nxt, final, reward, term, trunc, done
 
+    def substep_given_noise(self, state, action, noise):
+        """One sub-step of a chunk WITHOUT auto-reset (maniskill_env.py:339-343: self.step(actions, auto_reset=False));
+        noise [B, obs+2] = eps[obs] | eps_r | u_term."""
+        obs = self.obs_dim
+        z = state @ self.w_s + action @ self.w_a
+        s = torch.tanh(z + self.noise_std * noise[:, :obs])
+        reward = -(s * s).sum(-1) / obs + self.reward_noise_std * noise[:, obs]
+        self.elapsed += 1
+        term = noise[:, obs + 1] < self.p_term
+        trunc = (self.elapsed >= self.max_episode_steps) if self.max_episode_steps > 0 else torch.zeros_like(term)
+        return s, reward, term, trunc
+
+    def chunk_step_multi(self, chunk_actions, noise=None):
+        """chunk_step for num_action_chunks = C > 1 (maniskill_env.py:327-375): C sub-steps, raw flags any-reduced over
+        the chunk and reported on its last sub-step, one auto-reset after the chunk.  noise [B, C*(obs+2) + obs]."""
+        B, C, _ = chunk_actions.shape
+        obs = self.obs_dim
+        if noise is None:
+            parts = []
+            for _ in range(C):
+                parts += [torch.randn(B, obs + 1, generator=self.gen), torch.rand(B, 1, generator=self.gen)]
+            parts.append(torch.randn(B, obs, generator=self.gen))
+            noise = torch.cat(parts, dim=1)
+        state = self.state
+        rewards, terms, truncs = [], [], []
+        for c in range(C):
+            state, r, t, tr = self.substep_given_noise(state, chunk_actions[:, c], noise[:, c * (obs + 2):(c + 1) * (obs + 2)])
+            rewards.append(r)
+            terms.append(t)
+            truncs.append(tr)
+        rewards = torch.stack(rewards, dim=1)
+        past_term = torch.stack(terms, dim=1).any(dim=1)
+        past_trunc = torch.stack(truncs, dim=1).any(dim=1)
+        past_done = past_term | past_trunc
+        final = state
+        nxt = state
+        if self.auto_reset:
+            nxt = torch.where(past_done.unsqueeze(-1), noise[:, C * (obs + 2):], state)
+            self.elapsed[past_done] = 0
+        chunk_term = torch.zeros(B, C, dtype=torch.bool)
+        chunk_trunc = torch.zeros(B, C, dtype=torch.bool)
+        chunk_term[:, -1] = past_term
+        chunk_trunc[:, -1] = past_trunc
+        self.state = nxt
+        return ([{"states": nxt}], rewards, chunk_term, chunk_trunc, [{"final_observation": {"states": final}}])
+
     def chunk_step(self, chunk_actions, noise=None):
         B = self.B
+        if chunk_actions.shape[1] != 1:
+            return self.chunk_step_multi(chunk_actions, noise)
         if noise is None:
             noise = torch.cat([torch.randn(B, self.obs_dim + 1, generator=self.gen),
                                torch.rand(B, 1, generator=self.gen),
@@ -85,7 +133,9 @@ class RunnerOracle:
         self.critic_warmup_steps = int(o.get("critic_warmup_steps", 0) or 0)  # fsdp_model_manager.py:88-93
         self.opt = self._build_optimizer(self.critic_warmup_steps > 0)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, O.lr_lambda(o, o["lr"]))
-        self.env = SyntheticEnvCPU(self.B, self.obs_dim, self.act_dim, et["max_episode_steps"], et["auto_reset"],
+        self.num_action_chunks = m.get("num_action_chunks", 1)
+        self.n_chunk_steps = self.T // self.num_action_chunks  # env_worker.py: max_steps_per_rollout_epoch // chunks
+        self.env = SyntheticEnvCPU(self.B, self.obs_dim, m["action_dim"], et["max_episode_steps"], et["auto_reset"],
                                    et.get("p_term", 0.005), et.get("noise_std", 0.1),
                                    et.get("reward_noise_std", 0.01), et.get("seed", 1234))
         self.gen = torch.Generator().manual_seed(cfg["actor"]["seed"])
@@ -116,15 +166,16 @@ class RunnerOracle:
     # -- rollout (env_worker.py:1059-1349 / huggingface_worker.py:678-781) -----------------------------
     @torch.no_grad()
     def rollout(self, policy_noise=None, env_noise=None):
-        """policy_noise [T+1,B,act] / env_noise [T,B,2*obs+2]: pre-drawn draws for parity tests."""
+        """policy_noise [nc+1,B,C*A] / env_noise [nc,B,2*obs+2] (C = 1) or [nc,B,C*(obs+2)+obs]: pre-drawn draws for the
+        parity tests; nc = chunk steps."""
         a = self.cfg["algorithm"]
         gamma, boot_always = a.get("gamma", 1), a.get("bootstrap_type", "standard") != "standard"
-        B, T = self.B, self.T
+        B, T, Cn = self.B, self.n_chunk_steps, self.num_action_chunks
         if self.obs is None or not self.env.auto_reset:  # bootstrap_step, env_worker.py:908-935
             self.obs, _ = self.env.reset()
         lists = {k: [] for k in ("rewards", "dones", "terminations", "truncations", "prev_values", "prev_logprobs",
                                  "states", "action")}
-        dones = torch.zeros(B, 1, dtype=torch.bool)
+        dones = torch.zeros(B, Cn, dtype=torch.bool)
         term, trunc = dones.clone(), dones.clone()
         rewards, final_obs = None, None
         for t in range(T + 1):
@@ -152,7 +203,7 @@ class RunnerOracle:
             lists["states"].append(states.contiguous())
             lists["action"].append(action.contiguous())
             obs_list, rewards, term, trunc, infos = self.env.chunk_step(
-                action.reshape(B, 1, -1), None if env_noise is None else env_noise[t])
+                action.reshape(B, Cn, -1), None if env_noise is None else env_noise[t])
             self.obs = obs_list[-1]
             dones = term | trunc
             final_obs = infos[-1]["final_observation"]

@@ -627,6 +627,17 @@ static long long* g_prof = nullptr;  // rb200_tc_h_debug
 
 int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn, cudaStream_t st) {
   if (ngroups < 1 || ngroups > 2 || K % BK != 0 || K <= 0 || M <= 0) return RB200_E_SHAPE;
+  // Two towers in one launch fill the tail wave of small per-rank batches; at large M the two interleaved operand /
+  // result streams cost HBM efficiency (measured on B200 at M = 262144: 346 us grouped vs 2 x 122 us back to back),
+  // so big problems run one launch per tower.  Debug flag 16 forces grouping, 32 forces splitting.
+  if (ngroups == 2) {
+    const int64_t tiles = (M + BM - 1) / BM;
+    const bool split = (rb::tc::g_debug_flags & 32) || (!(rb::tc::g_debug_flags & 16) && tiles >= 4 * (int64_t)rb::sm_count());
+    if (split) {
+      int e = launch(L, 1, M, K, epi, b_mn, st);
+      return e ? e : launch(L + 1, 1, M, K, epi, b_mn, st);
+    }
+  }
   if (b_mn && K != BN) return RB200_E_SHAPE;  // dgrad of the square hidden layers
   GemmParams P{};
   P.M = M; P.K = K; P.epi = epi; P.b_mn = b_mn; P.ngroups = ngroups; P.flags = rb::tc::g_debug_flags;

@@ -34,6 +34,7 @@ class SyntheticVectorEnv:
         self._z = torch.empty(B, obs_dim, device=self.device)
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)  # device RNG step counter
         self._reset_gen = torch.Generator(device=self.device).manual_seed(self.seed + 1)
+        self._chunk_scratch = None
 
     def reset(self):
         self.state.normal_(generator=self._reset_gen)  # one-off initialisation, not on the hot path
@@ -51,11 +52,37 @@ class SyntheticVectorEnv:
             L.ptr(self.counter), L.stream_ptr()), "synth_env_step")
         L.check(lib.rb200_counter_add(L.ptr(self.counter), 1, L.stream_ptr()), "counter_add")
 
+    def chunk_step_into(self, state, chunk_actions, next_state, final_obs, rewards, term, trunc, done, noise=None):
+        """num_action_chunks = C > 1 (maniskill_env.py:327-375): C sub-steps without auto-reset, flags any-reduced onto
+        the last sub-step, one auto-reset after the chunk.  chunk_actions [B, C*A]; rewards / term / trunc / done [B, C]
+        rows of the rollout buffer; noise: optional pre-drawn [B, C*(obs+2) + obs]."""
+        lib = L.load()
+        B, CA = chunk_actions.shape
+        Cn = CA // self.action_dim
+        if self._chunk_scratch is None:
+            self._chunk_scratch = torch.empty(3, B, self.obs_dim, device=self.device)
+        L.check(lib.rb200_synth_env_chunk_step(
+            L.ptr(self.w_s), L.ptr(self.w_a), L.ptr(state), L.ptr(chunk_actions), L.ptr(noise), L.ptr(next_state),
+            L.ptr(final_obs), L.ptr(rewards), L.ptr(term), L.ptr(trunc), L.ptr(done), L.ptr(self.elapsed),
+            L.ptr(self._chunk_scratch), self.num_envs, self.obs_dim, self.action_dim, Cn, self.max_episode_steps,
+            int(self.auto_reset), self.p_term, self.noise_std, self.reward_noise_std, self.seed, L.ptr(self.counter),
+            L.stream_ptr()), "synth_env_chunk_step")
+        L.check(lib.rb200_counter_add(L.ptr(self.counter), 1, L.stream_ptr()), "counter_add")
+
     def chunk_step(self, chunk_actions, noise=None):
         B, C, A = chunk_actions.shape
-        if C != 1:
-            raise NotImplementedError("SyntheticVectorEnv implements num_action_chunks == 1 (MLP policy config)")
         dev = self.device
+        if C != 1:
+            nxt = torch.empty_like(self.state)
+            final = torch.empty_like(self.state)
+            rew = torch.empty(B, C, dtype=torch.float32, device=dev)
+            term = torch.empty(B, C, dtype=torch.uint8, device=dev)
+            trunc, done = torch.empty_like(term), torch.empty_like(term)
+            self.chunk_step_into(self.state, chunk_actions.reshape(B, C * A).contiguous(), nxt, final, rew, term, trunc,
+                                 done, noise)
+            self.state = nxt
+            return ([{"states": nxt}], rew, term.view(torch.bool), trunc.view(torch.bool),
+                    [{"final_observation": {"states": final}}])
         nxt = torch.empty_like(self.state)
         final = torch.empty_like(self.state)
         rew = torch.empty(B, dtype=torch.float32, device=dev)

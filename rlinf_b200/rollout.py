@@ -97,18 +97,21 @@ def convert_trajectories_to_batch(trajectories: list) -> dict:
 
 
 class RolloutBuffer:
-    def __init__(self, T, B, obs_dim, act_dim, value_dim=1, device=None):
+    def __init__(self, T, B, obs_dim, act_dim, value_dim=1, device=None, num_action_chunks=1):
+        """T = CHUNK steps (n_chunk_steps = env steps // num_action_chunks); act_dim = num_action_chunks * action_dim.
+        rewards / dones / terminations / truncations carry one column per sub-step of a chunk."""
         dev = device or L.default_device()
         self.T, self.B, self.obs_dim, self.act_dim, self.value_dim = T, B, obs_dim, act_dim, value_dim
+        self.num_action_chunks = Cn = int(num_action_chunks)
         f32, u8 = torch.float32, torch.uint8
         self.states = torch.zeros(T + 1, B, obs_dim, dtype=f32, device=dev)  # row T = bootstrap observation
         self.actions = torch.zeros(T, B, act_dim, dtype=f32, device=dev)
         self.prev_logprobs = torch.zeros(T, B, act_dim, dtype=f32, device=dev)
         self.prev_values = torch.zeros(T + 1, B, value_dim, dtype=f32, device=dev)
-        self.rewards = torch.zeros(T, B, 1, dtype=f32, device=dev)
-        self.dones = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
-        self.terminations = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
-        self.truncations = torch.zeros(T + 1, B, 1, dtype=u8, device=dev)
+        self.rewards = torch.zeros(T, B, Cn, dtype=f32, device=dev)
+        self.dones = torch.zeros(T + 1, B, Cn, dtype=u8, device=dev)
+        self.terminations = torch.zeros(T + 1, B, Cn, dtype=u8, device=dev)
+        self.truncations = torch.zeros(T + 1, B, Cn, dtype=u8, device=dev)
         self.final_obs = torch.zeros(B, obs_dim, dtype=f32, device=dev)
         self.final_values = torch.zeros(B, value_dim, dtype=f32, device=dev)
 
@@ -184,6 +187,12 @@ class RolloutWorker:
         # persistent fused kernel: needs the synthetic env's dynamics (w_s, w_a) and a supported MLP shape
         # "auto" | "tc" (tensor-core persistent kernel) | True / "simt" (fp32 SIMT persistent kernel) | False (per-kernel graph)
         mode = cfg.rollout.get("fused_kernel", "auto")
+        self.num_action_chunks = int(getattr(buffer, "num_action_chunks", 1))
+        if self.num_action_chunks > 1:
+            if mode in ("tc", "simt", True):
+                raise ValueError("the persistent rollout kernels implement num_action_chunks == 1; chunked policies use "
+                                 "the per-kernel loop (rollout.fused_kernel: false / auto)")
+            mode = False
         on_dev_env = policy.device.type == "cuda" and hasattr(env, "w_s") and hasattr(env, "w_a")
         supported = (on_dev_env
                      and L.load().rb200_rollout_fused_supported(C.byref(policy.layout), int(buffer.B)) == 0)
@@ -266,6 +275,8 @@ class RolloutWorker:
         T, B = buf.T, buf.B
         st = L.stream_ptr()
         pol.mark_params_changed()  # the weight split refresh is always part of the (captured) rollout
+        if self.num_action_chunks > 1:
+            return self._chunked_rollout(policy_noise, env_noise)
         main, side = torch.cuda.current_stream(), self._side
         side_busy = False
         for t in range(T):
@@ -295,6 +306,30 @@ class RolloutWorker:
         # final extra inference for the bootstrap value row T (env_worker.py:1237-1306)
         if pol.value_dim > 0:
             pol.value(buf.states[T], out=buf.prev_values[T])
+
+    def _chunked_rollout(self, policy_noise=None, env_noise=None):
+        """num_action_chunks = C > 1: one policy inference per CHUNK step, C env sub-steps per chunk (chunk_step contract,
+        maniskill_env.py:327-375), bootstrap on the chunk's last sub-step (compute_bootstrap_rewards, env_worker.py:
+        719-758).  policy_noise [nc, B, C*A], env_noise [nc, B, C*(obs+2) + obs]."""
+        lib = L.load()
+        buf, pol, env = self.buf, self.policy, self.env
+        nc, B, Cn = buf.T, buf.B, self.num_action_chunks
+        st = L.stream_ptr()
+        for n in range(nc):
+            pol.sample(buf.states[n], noise=None if policy_noise is None else policy_noise[n], seed=self.seed, offset=0,
+                       counter=self.counter, out=(buf.actions[n], buf.prev_logprobs[n], buf.prev_values[n]))
+            L.check(lib.rb200_counter_add(L.ptr(self.counter), 1, st), "counter_add")
+            env.chunk_step_into(buf.states[n], buf.actions[n], buf.states[n + 1], buf.final_obs, buf.rewards[n],
+                                buf.terminations[n + 1], buf.truncations[n + 1], buf.dones[n + 1],
+                                noise=None if env_noise is None else env_noise[n])
+            if self.auto_reset and pol.value_dim > 0:
+                flag = buf.truncations[n + 1] if self.bootstrap_type == "standard" else buf.dones[n + 1]
+                pol.value(buf.final_obs, out=buf.final_values)
+                L.check(lib.rb200_bootstrap_rewards_ld(
+                    C.c_void_p(buf.rewards[n].data_ptr() + 4 * (Cn - 1)), Cn, L.ptr(buf.final_values), pol.value_dim,
+                    C.c_void_p(flag.data_ptr() + (Cn - 1)), Cn, B, self.gamma, st), "bootstrap_rewards_ld")
+        if pol.value_dim > 0:
+            pol.value(buf.states[nc], out=buf.prev_values[nc])
 
     def generate(self):
         """One rollout epoch of T steps into the buffer (all on the current stream, no host sync)."""

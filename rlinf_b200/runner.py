@@ -30,14 +30,13 @@ class EmbodiedRunner:
         self.env_start, self.B = shard_envs(et.total_num_envs, self.world_size, self.rank,
                                             cfg.algorithm.get("group_size", 1))  # envs owned by this rank
         self.T = et.max_steps_per_rollout_epoch
-        if m.get("num_action_chunks", 1) != 1:
-            # the device rollout (buffer rows, env kernels, fused kernel) is written for one action per env step; the
-            # advantage / loss kernels handle num_action_chunks > 1 (tested), the synthetic rollout does not
-            raise NotImplementedError("EmbodiedRunner's device rollout implements num_action_chunks == 1 (MLP policy "
-                                      "configs); feed chunked batches to EmbodiedActor directly")
+        Cn = int(m.get("num_action_chunks", 1))
+        if self.T % Cn != 0:
+            raise ValueError(f"max_steps_per_rollout_epoch {self.T} is not a multiple of num_action_chunks {Cn}")
+        self.n_chunk_steps = self.T // Cn  # env_worker.py: n_chunk_steps = max_steps_per_rollout_epoch // num_action_chunks
         self.actor = EmbodiedActor(cfg, rank=self.rank, world_size=self.world_size, process_group=process_group)
         pol = self.actor.model
-        self.env = SyntheticVectorEnv(self.B, m.obs_dim, m.action_dim * m.get("num_action_chunks", 1),
+        self.env = SyntheticVectorEnv(self.B, m.obs_dim, m.action_dim,  # the env takes ONE action per sub-step
                                       et.max_episode_steps, auto_reset=et.auto_reset, p_term=et.get("p_term", 0.005),
                                       noise_std=et.get("noise_std", 0.1),
                                       reward_noise_std=et.get("reward_noise_std", 0.01),
@@ -46,8 +45,9 @@ class EmbodiedRunner:
         g = torch.Generator().manual_seed(et.get("seed", 1234))
         import math
         self.env.w_s.copy_(torch.randn(m.obs_dim, m.obs_dim, generator=g) / math.sqrt(m.obs_dim))
-        self.env.w_a.copy_(torch.randn(pol.act_dim, m.obs_dim, generator=g) / math.sqrt(pol.act_dim))
-        self.buffer = RolloutBuffer(self.T, self.B, m.obs_dim, pol.act_dim, max(pol.value_dim, 1))
+        self.env.w_a.copy_(torch.randn(m.action_dim, m.obs_dim, generator=g) / math.sqrt(m.action_dim))
+        self.buffer = RolloutBuffer(self.n_chunk_steps, self.B, m.obs_dim, pol.act_dim, max(pol.value_dim, 1),
+                                    num_action_chunks=Cn)
         self.rollout = RolloutWorker(cfg, pol, self.env, self.buffer)
         self.global_step = 0
         if self.world_size > 1:  # same initial weights everywhere (rank 0's)
