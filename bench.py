@@ -381,7 +381,8 @@ def kernel_rooflines(a, peaks, torch):
     out["gather_ppo_loss_fwd_bwd"] = {"bound": "hbm", "achieved": bytes_ppo / t / 1e9, "peak": peaks["hbm_gbs"],
                                       "unit": "GB/s", "frac": bytes_ppo / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                       "us_per_launch": t * 1e6, "algorithmic_bytes": bytes_ppo,
-                                      "launch_note": "memset + main + finalise nodes; rollout rows gathered through idx"}
+                                      "launch_note": "ONE kernel (the last CTA finalises and clears the workspace); rollout rows gathered "
+                                                     "through idx: each gathered 4-byte scalar pulls a 32-byte sector"}
     del cur, idxs, old, adv, ret, pv, perm
 
     # ---- tcgen05 fp16-split GEMMs of the MLP towers at the mini-batch shape (the shipped kernels, csrc/tc_gemm_h.cu) ----
