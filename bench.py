@@ -385,6 +385,31 @@ def kernel_rooflines(a, peaks, torch):
                                                      "through idx: each gathered 4-byte scalar pulls a 32-byte sector"}
     del cur, idxs, old, adv, ret, pv, perm
 
+    # ---- logits -> logprob / entropy, vocabulary-sized rows: N*V*4 bytes forward, 2x backward ----
+    Nl, V = 4096, 32000  # 524 MB of fp32 logits: every launch streams from HBM
+    lg = torch.randn(Nl, V, device=dev)
+    dlg = torch.empty_like(lg)
+    tg = torch.randint(0, V, (Nl,), device=dev)
+    lpo, eno, lso = (torch.empty(Nl, device=dev) for _ in range(3))
+    g1, g2 = torch.randn(Nl, device=dev), torch.randn(Nl, device=dev)
+
+    def lg_fwd():
+        L.check(lib.rb200_logits_logprob_entropy_fwd(L.ptr(lg), 0, L.ptr(tg), Nl, Nl, 0, V, V, 0, V, 1.25, L.ptr(lpo),
+                                                     L.ptr(eno), L.ptr(lso), L.stream_ptr()), "logits_fwd")
+
+    def lg_bwd():
+        L.check(lib.rb200_logits_logprob_entropy_bwd(L.ptr(lg), 0, L.ptr(tg), Nl, Nl, 0, V, V, 0, V, 1.25, L.ptr(lso),
+                                                     L.ptr(eno), L.ptr(g1), L.ptr(g2), L.ptr(dlg), 0, V,
+                                                     L.stream_ptr()), "logits_bwd")
+
+    lg_fwd()
+    for key, fn, nbytes in (("logits_logprob_entropy_fwd", lg_fwd, Nl * V * 4), ("logits_logprob_entropy_bwd", lg_bwd, 2 * Nl * V * 4)):
+        t = time_graph(fn, 1)
+        out[key] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": nbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": t * 1e6,
+                    "algorithmic_bytes": nbytes, "rows": Nl, "vocab": V}
+    del lg, dlg
+
     # ---- tcgen05 fp16-split GEMMs of the MLP towers at the mini-batch shape (the shipped kernels, csrc/tc_gemm_h.cu) ----
     n = mb
     K = 256

@@ -39,7 +39,8 @@ constexpr int kNE = 32;        // environments per CTA (MMA N)
 constexpr int kMaxActTc = 8;   // action dims held in shared memory
 constexpr int kMaxObsTc = 128; // one M tile of the env product
 constexpr int kStageBytes = 16384, kHalfTile = 8192;  // [128 rows x 32 k] fp16 hi | lo
-constexpr int kStages = 5;
+constexpr int kStages = 5;  // (the MMA issue loop switches over the 5 slots)
+static_assert(kStages == 5, "rollout_tc issue switch");
 constexpr int kThreads = 14 * 32;
 constexpr int kWScaleLog2 = 10;  // weights are stored as fp16 (hi, lo) of w * 2^10
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;
@@ -148,6 +149,17 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                    smem_u32(smem_dst)),
                "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one lane of a converged warp; the compiler emits the tcgen05 instructions under it directly (a plain `lane == 0`
+// branch makes it wrap every UTCHMMA in an elect / loop-over-active-lanes sequence: ~9 instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -507,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
       stream(sg.v2, 16);
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (the whole warp runs the schedule, one elected lane issues) =================
+    {
       // The N = 32 MMAs are short (16-32 clk of tensor work): this single thread's issue rate is what bounds the
       // tensor phase, so the loop is kept lean - ring slot / phase by counters, descriptors as {lo, hi} words with
       // only the 14-bit address field changing (K-major SWIZZLE_64B: LBO 1, SBO 512 B, version 1, layout 4).
@@ -517,6 +529,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
       constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);  // bits 32..63 of desc_k_sw64
       auto desc = [&](uint32_t addr) -> uint64_t {
         return ((uint64_t)kDescHi << 32) | (uint64_t)(((addr & 0x3ffffu) >> 4) | (1u << 16));
+      };
+      // descriptors of the weight halves of every ring slot, computed once: the issue loop switches on the slot so
+      // that they are plain registers (one thread issues all 504 MMAs of a step; its instruction count per MMA is what
+      // bounds the tensor phase - the tensor pipe itself is ~12 % busy)
+      uint64_t ad_hi[kStages], ad_lo[kStages];
+#pragma unroll
+      for (int i = 0; i < kStages; ++i) {
+        ad_hi[i] = desc(ring_a + i * kStageBytes);
+        ad_lo[i] = desc(ring_a + i * kStageBytes + kHalfTile);
+      }
+      auto issue6 = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                        uint32_t acc0) {
+        mma_f16(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+        mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+        mma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+        mma_f16(d_tmem, a_lo + 2, b_hi + 2, idesc, 1u);  // next 16 fp16 = 32 B along the 64-B row
+        mma_f16(d_tmem, a_hi + 2, b_lo + 2, idesc, 1u);
+        mma_f16(d_tmem, a_hi + 2, b_hi + 2, idesc, 1u);
       };
       // one layer: D[tile m] (TMEM columns d_col + m*N) = W tile m [128 x 32*nkb] . operand[N rows x 32*nkb]^T
       auto seg = [&](int ntile, int nkb, uint32_t b_hi_addr, uint32_t b_half, uint32_t b_kb_stride, uint32_t d_col, int N) {
@@ -530,17 +560,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
             const uint32_t d_tmem = tmem_base + d_col + (uint32_t)(m * N);
             wait_bar<PROF>(&ms->full[slot], ph, pc[1]);
             fence_after_sync();
-            const uint32_t sa = ring_a + slot * kStageBytes;
-            const uint64_t a_hi = desc(sa), a_lo = desc(sa + kHalfTile);
-            if (!(dbg & 2)) {  // (ablation: no tensor-core work)
-              mma_f16(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
-              mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-              mma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
-              mma_f16(d_tmem, a_lo + 2, b_hi + 2, idesc, 1u);  // next 16 fp16 = 32 B along the 64-B row
-              mma_f16(d_tmem, a_hi + 2, b_lo + 2, idesc, 1u);
-              mma_f16(d_tmem, a_hi + 2, b_hi + 2, idesc, 1u);
+            __syncwarp();
+            if (elect_one()) {
+              if (!(dbg & 2)) {  // (ablation: no tensor-core work)
+                switch (slot) {
+                  case 0: issue6(d_tmem, ad_hi[0], ad_lo[0], b_hi, b_lo, idesc, acc0); break;
+                  case 1: issue6(d_tmem, ad_hi[1], ad_lo[1], b_hi, b_lo, idesc, acc0); break;
+                  case 2: issue6(d_tmem, ad_hi[2], ad_lo[2], b_hi, b_lo, idesc, acc0); break;
+                  case 3: issue6(d_tmem, ad_hi[3], ad_lo[3], b_hi, b_lo, idesc, acc0); break;
+                  default: issue6(d_tmem, ad_hi[4], ad_lo[4], b_hi, b_lo, idesc, acc0); break;
+                }
+              }
+              mma_commit(&ms->empty[slot]);
             }
-            mma_commit(&ms->empty[slot]);
             if (++slot == kStages) {
               slot = 0;
               ph ^= 1u;
@@ -582,7 +614,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const TcArgs p)
           seg(sgi == 0 ? 1 : 2, layer == 0 ? sg.nkb0 : 8, layer == 0 ? obuf_a : (is_v ? vbuf_a : abuf_a),
               layer == 0 ? ob_half : (is_v ? (uint32_t)kVbufHalf : (uint32_t)kAbufHalf),
               (layer == 0 || is_v) ? 4096u : 2048u, sgi == 0 ? kAccEnv : (is_v ? kAccV : kAccA), is_v ? nv : kNE);
-          mma_commit(sgi == 0 ? &ms->acc_env : (is_v ? &ms->acc_v : &ms->acc_a));
+          __syncwarp();
+          if (elect_one()) mma_commit(sgi == 0 ? &ms->acc_env : (is_v ? &ms->acc_v : &ms->acc_a));
         }
       }
     }

@@ -33,9 +33,11 @@ constexpr int kA32 = BM * BK * 4;   // 16 KB fp32 landing tile of the streamed o
 constexpr int kA16 = BM * BK * 2;   //  8 KB per fp16 half
 constexpr int kB16 = BN * BK * 2;   // 16 KB per fp16 half of the weight tile
 constexpr int kStageBytes = kA32 + 2 * kA16 + 2 * kB16;  // 64 KB
-constexpr int kXfWarps = 4;
-constexpr int kThreads = 32 * (2 + kXfWarps + 4);  // producer, MMA, transform, epilogue = 320
-constexpr int kStagingBytes = 4 * 2 * 4096;
+constexpr int kXfWarpsDefault = 4;  // transform warps per CTA: template parameter XF of the forward / dgrad kernel (4 or 8)
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter, 128 of the 256 output columns each: the bias+tanh / (1-h^2)
+                              // epilogue of one warp per scheduler took 7.8 k cycles per tile against 6.1 k of MMA
+constexpr int threads_for(int xf) { return 32 * (2 + xf + kEpiWarps); }  // producer, MMA, transform, epilogue
+constexpr int kStagingBytes = kEpiWarps * 4096;  // one [32 x 32] fp32 staging tile per epilogue warp
 constexpr int kTmemCols = 512;
 constexpr int kWeightScaleLog2 = 10;  // weights are stored as fp16 (hi, lo) of w * 2^10 (|w| <~ 1: both halves normal)
 
@@ -190,8 +192,9 @@ struct GemmParams {
   long long* prof;  // [16] (PROF instantiation only)
 };
 
-template <bool PROF>
-__global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_constant__ GemmParams P) {
+template <bool PROF, int kXfWarps>
+__global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int kThreads = threads_for(kXfWarps);
   long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       tma::mbar_init(&bars->tmem_full[b], 1);
-      tma::mbar_init(&bars->tmem_empty[b], 4);
+      tma::mbar_init(&bars->tmem_empty[b], kEpiWarps);
     }
     tma::fence_barrier_init();
   }
@@ -328,7 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
     // ================= epilogue warps =================
     const int q = warp & 3;
     const int ew = warp - (2 + kXfWarps);
-    float4 (*stg)[32][8] = reinterpret_cast<float4 (*)[32][8]>(staging + ew * 8192);
+    const int c_lo = (ew >> 2) * (BN / 2);  // this warp's half of the output columns
+    float4 (*sh)[8] = reinterpret_cast<float4 (*)[8]>(staging + ew * 4096);
     if (lane == 0) tma::prefetch_desc(&P.c[grp]);
     const int rs = lane >> 3, c4 = lane & 7;
     float4 hp[8];
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
         hp[i] = gr < P.M ? __ldg(reinterpret_cast<const float4*>(G.h + gr * BN + cc) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (P.epi == rb::tc::EPI_TANHGRAD && (int64_t)cta < n_tiles) load_h((int64_t)cta * BM + q * 32, 0);
+    if (P.epi == rb::tc::EPI_TANHGRAD && (int64_t)cta < n_tiles) load_h((int64_t)cta * BM + q * 32, c_lo);
     float vmax = 0.f;
     uint32_t tcount = 0;
     for (int64_t tile = cta; tile < n_tiles; tile += n_cta, ++tcount) {
@@ -351,9 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
       const int64_t row0 = tile * BM + q * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float4 (*sh)[8] = stg[(c0 >> 5) & 1];
-        if (lane == 0) tma::store_wait_read1();
+      for (int c0 = c_lo; c0 < c_lo + BN / 2; c0 += 32) {
+        if (lane == 0) tma::store_wait_read();  // the previous tile store has finished reading the staging tile
         __syncwarp();
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
@@ -364,8 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_h_gemm_kernel(const __grid_con
             sh[rr][c4 ^ (rr & 7)] = hp[i];
           }
           __syncwarp();
-          if (c0 + 32 < BN) load_h(row0, c0 + 32);
-          else if (tile + n_cta < n_tiles) load_h((tile + n_cta) * BM + q * 32, 0);
+          if (c0 + 32 < c_lo + BN / 2) load_h(row0, c0 + 32);
+          else if (tile + n_cta < n_tiles) load_h((tile + n_cta) * BM + q * 32, c_lo);
         }
         tmem_ld_wait();
 #pragma unroll
@@ -627,18 +630,13 @@ static long long* g_prof = nullptr;  // rb200_tc_h_debug
 
 int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn, cudaStream_t st) {
   if (ngroups < 1 || ngroups > 2 || K % BK != 0 || K <= 0 || M <= 0) return RB200_E_SHAPE;
-  // Two towers in one launch fill the tail wave of small per-rank batches; at large M the two interleaved operand /
-  // result streams cost HBM efficiency (measured on B200 at M = 262144: 346 us grouped vs 2 x 122 us back to back),
-  // so big problems run one launch per tower.  Debug flag 16 forces grouping, 32 forces splitting.
-  if (ngroups == 2) {
-    const int64_t tiles = (M + BM - 1) / BM;
-    const bool split = (rb::tc::g_debug_flags & 32) || (!(rb::tc::g_debug_flags & 16) && tiles >= 4 * (int64_t)rb::sm_count());
-    if (split) {
-      int e = launch(L, 1, M, K, epi, b_mn, st);
-      return e ? e : launch(L + 1, 1, M, K, epi, b_mn, st);
-    }
+  // Two towers in one launch: measured on B200 (profiles/r02_tc_h_gemm_grouping.txt) grouped is never slower than one
+  // launch per tower (1.18 vs 1.21 ms per 6-GEMM forward at 262144 rows, 0.21 vs 0.24 ms at 32768 where it fills the
+  // tail wave).  Debug flag 32 forces one launch per tower.
+  if (ngroups == 2 && (rb::tc::g_debug_flags & 32)) {
+    int e = launch(L, 1, M, K, epi, b_mn, st);
+    return e ? e : launch(L + 1, 1, M, K, epi, b_mn, st);
   }
-  if (b_mn && K != BN) return RB200_E_SHAPE;  // dgrad of the square hidden layers
   GemmParams P{};
   P.M = M; P.K = K; P.epi = epi; P.b_mn = b_mn; P.ngroups = ngroups; P.flags = rb::tc::g_debug_flags;
   for (int g = 0; g < ngroups; ++g) {
@@ -663,9 +661,11 @@ int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn
   constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
   static_assert(kSmem <= 232448, "tc_h_gemm_kernel shared memory");
   if (!attr_done) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(tc_h_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      ce = cudaFuncSetAttribute(tc_h_gemm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_h_gemm_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
     attr_done = true;
   }
@@ -675,8 +675,11 @@ int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn
   int per_group = sms / ngroups;
   if (per_group > n_tiles) per_group = (int)n_tiles;
   if (per_group < 1) per_group = 1;
-  if (g_prof) tc_h_gemm_kernel<true><<<per_group * ngroups, kThreads, kSmem, st>>>(P);
-  else tc_h_gemm_kernel<false><<<per_group * ngroups, kThreads, kSmem, st>>>(P);
+  // transform warps: 4 (one per scheduler) or 8 (debug flag 64) - see DESIGN.md section 4
+  const bool xf8 = ((rb::tc::g_debug_flags & 64) != 0) != (kXfWarpsDefault == 8);
+  if (g_prof) tc_h_gemm_kernel<true, 4><<<per_group * ngroups, threads_for(4), kSmem, st>>>(P);
+  else if (xf8) tc_h_gemm_kernel<false, 8><<<per_group * ngroups, threads_for(8), kSmem, st>>>(P);
+  else tc_h_gemm_kernel<false, 4><<<per_group * ngroups, threads_for(4), kSmem, st>>>(P);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;

@@ -8,7 +8,7 @@ for n in (262144, 131072, 65536, 32768):
     pol = MLPPolicy(obs_dim=128, action_dim=8, seed=0)
     states = torch.randn(n, 128, device='cuda'); action = torch.randn(n, 8, device='cuda')
     dl = torch.randn(n, 8, device='cuda') / n; dv = torch.randn(n, 1, device='cuda') / n
-    for name, fl in (("auto", 0), ("grouped", 16), ("split", 32)):
+    for name, fl in (("default", 0), ("split", 32), ("xf8", 64)):
         lib.rb200_debug_set_flags(fl)
         pol.mark_params_changed()
         for _ in range(2):
