@@ -324,7 +324,7 @@ int rb200_tc_wgrad(const float* Z, const float* H, float* dW, int64_t n, int IN,
                    rb200_stream_t stream);
 /* round 2: the same two unit-test entries for the fp16-split kernel::f16 kernels (csrc/tc_gemm_h.cu).
  * mode 0: C = A[M,K] . B[256,K]^T; mode 1 (dgrad form, K = 256): C = A[M,256] . B[256,256].  amax: device float holding
- * max|A| (or max|Z|), NULL = no operand scaling.  work: >= 256*K floats. */
+ * max|A| (or max|Z|), NULL = no operand scaling.  work: >= 512*K floats (packed fp16 weight tiles: forward + dgrad pack). */
 int rb200_tc_gemm_h(const float* A, const float* B, float* C, int64_t M, int K, int mode, const float* amax,
                     float* work, rb200_stream_t stream);
 int rb200_tc_wgrad_h(const float* Z, const float* H, float* dW, int64_t n, int IN, const float* amax,

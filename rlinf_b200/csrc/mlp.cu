@@ -491,8 +491,9 @@ int tower_backward(const float* X, const int64_t* idx, int64_t n, int in_dim, co
 // debug flag bit 3 (value 8) selects the round-1 3xTF32 kernels instead.
 inline bool half_mode() { return (rb::tc::g_debug_flags & 8) == 0; }
 
-struct TowerWH {  // fp16 (hi, lo) copies of w * 2^10, [256 out, in] as stored; typed float* (they live in the wsplit buffer)
-  const float *w0h, *w0l, *w1h, *w1l, *w2h, *w2l;
+struct TowerWH {  // packed fp16 (hi, lo) tiles of w * 2^10 (rb::tch::split_weights); typed float* (they live in the wsplit buffer)
+  const float *w0f, *w1f, *w2f;  // forward packs of layers 0..2
+  const float *w1d, *w2d;        // dgrad packs of the square layers
 };
 
 struct TowerIO {  // one tower of a grouped forward / backward
@@ -511,15 +512,15 @@ int towers_forward_h(const float* X, const int64_t* idx, int64_t n, int in_dim, 
   const bool l0_tc = idx == nullptr && (in_dim % rb::tc::BK == 0);
   rb::tch::GemmLaunch g[2];
   if (l0_tc) {
-    for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{X, t[i].wh.w0h, t[i].wh.w0l, t[i].H1, t[i].w.b0, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{X, t[i].wh.w0f, nullptr, t[i].H1, t[i].w.b0, nullptr, nullptr, nullptr, nullptr};
     if ((e = rb::tch::launch(g, nt, n, in_dim, rb::tc::EPI_BIAS_TANH, 0, st))) return e;
   } else {
     for (int i = 0; i < nt; ++i)
       if ((e = layer_forward(X, idx, n, in_dim, t[i].w.w0, t[i].w.b0, nullptr, nullptr, t[i].H1, st))) return e;
   }
-  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H1, t[i].wh.w1h, t[i].wh.w1l, t[i].H2, t[i].w.b1, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H1, t[i].wh.w1f, nullptr, t[i].H2, t[i].w.b1, nullptr, nullptr, nullptr, nullptr};
   if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_BIAS_TANH, 0, st))) return e;
-  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H2, t[i].wh.w2h, t[i].wh.w2l, t[i].H3, t[i].w.b2, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < nt; ++i) g[i] = rb::tch::GemmLaunch{t[i].H2, t[i].wh.w2f, nullptr, t[i].H3, t[i].w.b2, nullptr, nullptr, nullptr, nullptr};
   return rb::tch::launch(g, nt, n, kH, rb::tc::EPI_BIAS_TANH, 0, st);
 }
 
@@ -532,13 +533,13 @@ int towers_backward_h(const float* X, const int64_t* idx, int64_t n, int in_dim,
   for (int i = 0; i < nt; ++i) w[i] = rb::tch::WgradLaunch{t[i].dZ3, t[i].H2, t[i].g_w2, t[i].amax};
   if ((e = rb::tch::wgrad(w, nt, n, kH, st))) return e;
   for (int i = 0; i < nt; ++i)
-    g[i] = rb::tch::GemmLaunch{t[i].dZ3, t[i].wh.w2h, t[i].wh.w2l, t[i].tA, nullptr, t[i].H2, t[i].g_b1, t[i].amax, t[i].amax + 1};
+    g[i] = rb::tch::GemmLaunch{t[i].dZ3, t[i].wh.w2d, nullptr, t[i].tA, nullptr, t[i].H2, t[i].g_b1, t[i].amax, t[i].amax + 1};
   if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_TANHGRAD, 1, st))) return e;
   // layer 1
   for (int i = 0; i < nt; ++i) w[i] = rb::tch::WgradLaunch{t[i].tA, t[i].H1, t[i].g_w1, t[i].amax + 1};
   if ((e = rb::tch::wgrad(w, nt, n, kH, st))) return e;
   for (int i = 0; i < nt; ++i)
-    g[i] = rb::tch::GemmLaunch{t[i].tA, t[i].wh.w1h, t[i].wh.w1l, t[i].tB, nullptr, t[i].H1, t[i].g_b0, t[i].amax + 1, t[i].amax + 2};
+    g[i] = rb::tch::GemmLaunch{t[i].tA, t[i].wh.w1d, nullptr, t[i].tB, nullptr, t[i].H1, t[i].g_b0, t[i].amax + 1, t[i].amax + 2};
   if ((e = rb::tch::launch(g, nt, n, kH, rb::tc::EPI_TANHGRAD, 1, st))) return e;
   // layer 0: dW0 += dZ1^T . X
   if (idx == nullptr && (in_dim % rb::tc::BK == 0) && in_dim <= 256) {
@@ -627,16 +628,18 @@ TowerWS tower_ws(const rb200_mlp_layout* L, const float* ws, bool value) {
   t.w1th = q + 4 * nn; t.w1tl = q + 5 * nn; t.w2th = q + 6 * nn; t.w2tl = q + 7 * nn;
   return t;
 }
-// fp16-split cache: per tower (value tower first) w0 hi|lo [256*obs halves each], w1 hi|lo, w2 hi|lo [65536 halves each];
-// it needs half the floats of the TF32 cache, so it lives in the same buffer
+// fp16-split cache, per tower (value tower first): forward packs of w0 [256*obs floats of storage], w1, w2 [65536 each],
+// then the dgrad packs of w1, w2; it needs less than the TF32 cache, so it lives in the same buffer
 TowerWH tower_wh(const rb200_mlp_layout* L, const float* ws, bool value) {
-  const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;  // elements
-  const int64_t per_tower = n0 + 2 * nn;                                // floats (hi + lo = 4 bytes per element)
+  const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;  // floats of storage (4 bytes per element: hi + lo)
+  const int64_t per_tower = n0 + 4 * nn;
   const float* b = ws + (value ? 0 : per_tower);
   TowerWH t;
-  t.w0h = b; t.w0l = b + n0 / 2;
-  t.w1h = b + n0; t.w1l = t.w1h + nn / 2;
-  t.w2h = b + n0 + nn; t.w2l = t.w2h + nn / 2;
+  t.w0f = b;
+  t.w1f = b + n0;
+  t.w2f = b + n0 + nn;
+  t.w1d = b + n0 + 2 * nn;
+  t.w2d = b + n0 + 3 * nn;
   return t;
 }
 }  // namespace
@@ -657,9 +660,10 @@ extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float*
       const TowerW w = tower_w(L, params, v == 0);
       const TowerWH t = tower_wh(L, wsplit, v == 0);
       const int64_t n0 = (int64_t)kH * L->obs_dim, nn = (int64_t)kH * kH;
-      sp[cnt++] = rb::tch::SplitSpec{w.w0, const_cast<float*>(t.w0h), const_cast<float*>(t.w0l), n0};
-      sp[cnt++] = rb::tch::SplitSpec{w.w1, const_cast<float*>(t.w1h), const_cast<float*>(t.w1l), nn};
-      sp[cnt++] = rb::tch::SplitSpec{w.w2, const_cast<float*>(t.w2h), const_cast<float*>(t.w2l), nn};
+      if (L->obs_dim % rb::tc::BK == 0)  // layer 0 runs on the tensor cores only then
+        sp[cnt++] = rb::tch::SplitSpec{w.w0, const_cast<float*>(t.w0f), nullptr, n0};
+      sp[cnt++] = rb::tch::SplitSpec{w.w1, const_cast<float*>(t.w1f), const_cast<float*>(t.w1d), nn};
+      sp[cnt++] = rb::tch::SplitSpec{w.w2, const_cast<float*>(t.w2f), const_cast<float*>(t.w2d), nn};
     }
     return rb::tch::split_weights(sp, cnt, st);
   }

@@ -28,11 +28,18 @@ using rb::tc::BK;
 using rb::tc::BM;
 using rb::tc::BN;
 
-constexpr int kStages = 3;
+// Two rings (round 2, second half).  The first version kept the fp32 landing tile, its fp16 halves and the weight
+// tile in ONE 64 KB stage, 3 stages deep: a stage stayed busy for load latency (~3000 clk under HBM load) + transform
+// (~700) + MMA (768), i.e. ~1500 clk per k-block against 768 of MMA (tools/gemm_role_probe.py).  Now the fp32 landing
+// tiles have their own deep ring (freed as soon as the transform has read them: 6 x 16 KB of activations in flight per
+// SM) and the MMA operands (A hi | lo written by the transform, weight hi | lo landed by TMA) a shallow one.
+constexpr int kAStages = 6;         // fp32 landing ring of the streamed operand
+constexpr int kBStages = 2;         // fp16 operand ring
 constexpr int kA32 = BM * BK * 4;   // 16 KB fp32 landing tile of the streamed operand
 constexpr int kA16 = BM * BK * 2;   //  8 KB per fp16 half
 constexpr int kB16 = BN * BK * 2;   // 16 KB per fp16 half of the weight tile
-constexpr int kStageBytes = kA32 + 2 * kA16 + 2 * kB16;  // 64 KB
+constexpr int kOpBytes = 2 * kA16 + 2 * kB16;               // 48 KB: A hi | A lo | W hi | W lo
+constexpr int kRingBytes = kAStages * kA32 + kBStages * kOpBytes;  // 192 KB
 constexpr int kXfWarpsDefault = 4;  // transform warps per CTA: template parameter XF of the forward / dgrad kernel (4 or 8)
 constexpr int kEpiWarps = 8;  // two per TMEM lane quarter, 128 of the 256 output columns each: the bias+tanh / (1-h^2)
                               // epilogue of one warp per scheduler took 7.8 k cycles per tile against 6.1 k of MMA
@@ -81,6 +88,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tma::smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tma::smem_u32(bar))
+               : "memory");
+}
 
 // ---- UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp; canonical layouts in
 //      cute/atom/mma_traits_sm100.hpp:167-203).  start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
@@ -149,6 +163,39 @@ __device__ __forceinline__ void split_tile(const uint8_t* __restrict__ src, uint
   }
 }
 
+// fp32 PLAIN row-major landing tile [32 samples x `cols` floats] (one TMA box per operand: 32 row requests of
+// 4*cols bytes instead of cols/32 boxes of 32 x 128 B) -> the same fp16 hi / lo groups split_tile produces:
+// [cols/32 groups][32 samples x 32 halfs] SWIZZLE_64B.  item = (sample r, 8 consecutive floats p): consecutive threads
+// read consecutive 32-byte pieces of a row (conflict-free LDS.128).
+template <int NT>
+__device__ __forceinline__ void split_rows_plain(const uint8_t* __restrict__ src, int cols, uint8_t* __restrict__ hi,
+                                                 uint8_t* __restrict__ lo, int t, float scale) {
+  const int ppr = cols >> 3;  // 8-float pieces per row
+  const int items = 32 * ppr;
+#pragma unroll 2
+  for (int i = t; i < items; i += NT) {
+    const int r = i / ppr, pc = i - r * ppr;
+    const uint8_t* sp = src + ((size_t)r * cols + pc * 8) * 4;
+    const float4 x0 = *reinterpret_cast<const float4*>(sp);
+    const float4 x1 = *reinterpret_cast<const float4*>(sp + 16);
+    const float v[8] = {x0.x * scale, x0.y * scale, x0.z * scale, x0.w * scale,
+                        x1.x * scale, x1.y * scale, x1.z * scale, x1.w * scale};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const int g = pc >> 2, cp = pc & 3;  // feature group of 32, 16-byte chunk inside its 64-byte row
+    const int doff = (g * 32 + r) * 64 + ((cp ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(hi + doff) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + doff) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // PROF instantiations (tools/gemm_role_probe.py): cycles each role of CTA 0 spends waiting / working
 template <bool PROF>
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long& acc) {
@@ -162,14 +209,16 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long lo
 }
 
 struct __align__(16) Barriers {
-  uint64_t full[kStages];
-  uint64_t xf[kStages];
-  uint64_t empty[kStages];
+  uint64_t full_a[kAStages];   // fp32 landing tile arrived (TMA tx bytes)
+  uint64_t empty_a[kAStages];  // transform warps have read it
+  uint64_t full_b[kBStages];   // weight halves arrived (TMA tx bytes)
+  uint64_t xf[kBStages];       // transform warps have written A hi | lo
+  uint64_t empty_b[kBStages];  // MMAs reading the operand slot have completed (tcgen05.commit)
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  alignas(16) float bias[BN];  // (read as float4: with kStages = 3 the members above end at byte 120) forward: the layer bias; dgrad: per-CTA column sums of the output (bias gradient of the producer)
+  alignas(16) float bias[BN];  // (read as float4) forward: the layer bias; dgrad: per-CTA column sums of the output (bias gradient of the producer)
 };
 
 struct Group {
@@ -181,7 +230,8 @@ struct Group {
 };
 
 struct GemmParams {
-  CUtensorMap a[2], bh[2], bl[2], c[2];
+  CUtensorMap a[2], c[2];
+  const uint8_t* wpack[2];  // packed weight tiles of each group (32 KB per k-block: hi | lo)
   Group g[2];
   int64_t M;
   int K;
@@ -199,7 +249,9 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* staging = smem + kStages * kStageBytes;
+  uint8_t* ring_a = smem;                       // kAStages x [128 rows x 32 fp32] SWIZZLE_128B
+  uint8_t* ring_b = smem + kAStages * kA32;     // kBStages x (A hi | A lo | W hi | W lo)
+  uint8_t* staging = smem + kRingBytes;
   Barriers* bars = reinterpret_cast<Barriers*>(staging + kStagingBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,10 +262,14 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
   const int n_kb = P.K / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      tma::mbar_init(&bars->full[s], 1);
+    for (int s = 0; s < kAStages; ++s) {
+      tma::mbar_init(&bars->full_a[s], 1);
+      tma::mbar_init(&bars->empty_a[s], kXfWarps);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      tma::mbar_init(&bars->full_b[s], 1);
       tma::mbar_init(&bars->xf[s], kXfWarps);
-      tma::mbar_init(&bars->empty[s], 1);
+      tma::mbar_init(&bars->empty_b[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       tma::mbar_init(&bars->tmem_full[b], 1);
@@ -239,37 +295,27 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
     // ================= TMA producer =================
     if (lane == 0) {
       tma::prefetch_desc(&P.a[grp]);
-      tma::prefetch_desc(&P.bh[grp]);
-      tma::prefetch_desc(&P.bl[grp]);
       const int64_t my_tiles = n_tiles > cta ? (n_tiles - cta + n_cta - 1) / n_cta : 0;
       const int64_t total = my_tiles * n_kb;
-      // L2 prefetch distance in k-blocks (debug flag bits 8-15 override: 255 = off)
-      int pf = (P.flags >> 8) & 0xff;
-      pf = pf == 0 ? 3 : (pf == 255 ? 0 : pf);
-      for (int64_t j = 0; j < pf && j < total; ++j)
-        tma::prefetch_2d(&P.a[grp], (int)(j % n_kb) * BK, (int)((cta + (j / n_kb) * n_cta) * BM));
-      for (int64_t j = 0; j < total; ++j) {
-        const uint32_t it = (uint32_t)j;
-        const int kb = (int)(j % n_kb);
-        const int m0 = (int)((cta + (j / n_kb) * n_cta) * BM);
-        const int64_t jp = j + pf;
-        if (jp < total) tma::prefetch_2d(&P.a[grp], (int)(jp % n_kb) * BK, (int)((cta + (jp / n_kb) * n_cta) * BM));
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        wait_bar<PROF>(&bars->empty[s], ph ^ 1u, pc[0]);
-        uint8_t* st = smem + s * kStageBytes;
-        uint8_t* sb = st + kA32 + 2 * kA16;
-        tma::mbar_arrive_expect_tx(&bars->full[s], kA32 + 2 * kB16);
-        tma::load_2d(st, &P.a[grp], kb * BK, m0, &bars->full[s]);  // rows >= M are zero-filled
-        if (!P.b_mn) {  // [256 rows x 32 k] boxes of the K-major weight copy
-          tma::load_2d(sb, &P.bh[grp], kb * BK, 0, &bars->full[s]);
-          tma::load_2d(sb + kB16, &P.bl[grp], kb * BK, 0, &bars->full[s]);
-        } else {        // MN-major: 4 boxes {64 in-columns, 32 out-rows} per half
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            tma::load_2d(sb + q * 4096, &P.bh[grp], q * 64, kb * BK, &bars->full[s]);
-            tma::load_2d(sb + kB16 + q * 4096, &P.bl[grp], q * 64, kb * BK, &bars->full[s]);
-          }
+      // two independent streams issued by one thread: poll both rings, load whichever has a free slot
+      int64_t ja = 0, jb = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      while (ja < total || jb < total) {
+        if (ja < total && tma::mbar_try_wait(&bars->empty_a[sa], pa ^ 1u)) {
+          const int kb = (int)(ja % n_kb);
+          const int m0 = (int)((cta + (ja / n_kb) * n_cta) * BM);
+          tma::mbar_arrive_expect_tx(&bars->full_a[sa], kA32);
+          tma::load_2d(ring_a + sa * kA32, &P.a[grp], kb * BK, m0, &bars->full_a[sa]);  // rows >= M are zero-filled
+          ++ja;
+          if (++sa == kAStages) { sa = 0; pa ^= 1u; }
+        }
+        if (jb < total && tma::mbar_try_wait(&bars->empty_b[sb], pb ^ 1u)) {
+          const int kb = (int)(jb % n_kb);
+          uint8_t* wdst = ring_b + sb * kOpBytes + 2 * kA16;
+          tma::mbar_arrive_expect_tx(&bars->full_b[sb], 2 * kB16);
+          bulk_load(wdst, P.wpack[grp] + (size_t)kb * (2 * kB16), 2 * kB16, &bars->full_b[sb]);  // hi | lo, one copy
+          ++jb;
+          if (++sb == kBStages) { sb = 0; pb ^= 1u; }
         }
       }
     }
@@ -285,14 +331,14 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
-          wait_bar<PROF>(&bars->full[s], ph, pc[2]);
+          const int s = it % kBStages;
+          const uint32_t ph = (it / kBStages) & 1u;
+          wait_bar<PROF>(&bars->full_b[s], ph, pc[2]);
           wait_bar<PROF>(&bars->xf[s], ph, pc[3]);
           fence_after_sync();
-          const uint32_t sa32 = tma::smem_u32(smem + s * kStageBytes);
-          const uint64_t a_hi = desc_k_sw64(sa32 + kA32), a_lo = desc_k_sw64(sa32 + kA32 + kA16);
-          const uint32_t sbase = sa32 + kA32 + 2 * kA16;
+          const uint32_t sa32 = tma::smem_u32(ring_b + s * kOpBytes);
+          const uint64_t a_hi = desc_k_sw64(sa32), a_lo = desc_k_sw64(sa32 + kA16);
+          const uint32_t sbase = sa32 + 2 * kA16;
           const uint64_t b_hi = P.b_mn ? desc_mn_sw128(sbase, 4096) : desc_k_sw64(sbase);
           const uint64_t b_lo = P.b_mn ? desc_mn_sw128(sbase + kB16, 4096) : desc_k_sw64(sbase + kB16);
 #pragma unroll
@@ -304,7 +350,7 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
             mma_f16(d_tmem, a_hi + ka, b_lo + kbo, idesc, 1u);
             mma_f16(d_tmem, a_hi + ka, b_hi + kbo, idesc, 1u);
           }
-          mma_commit(&bars->empty[s]);
+          mma_commit(&bars->empty_b[s]);
         }
         mma_commit(&bars->tmem_full[buf]);
       }
@@ -312,19 +358,23 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
   } else if (warp < 2 + kXfWarps) {
     // ================= transform warps: fp32 A tile -> (A_hi, A_lo) fp16 tiles =================
     const int t = threadIdx.x - 64;
-    uint32_t it = 0;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     for (int64_t tile = cta; tile < n_tiles; tile += n_cta) {
-      for (int kb = 0; kb < n_kb; ++kb, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        wait_bar<PROF>(&bars->full[s], ph, pc[4]);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        wait_bar<PROF>(&bars->full_a[sa], pa, pc[4]);           // the fp32 tile has landed
+        wait_bar<PROF>(&bars->empty_b[sb], pb ^ 1u, pc[0]);     // the operand slot's previous MMAs are done
         const long long t_w0 = PROF ? clock64() : 0;
-        uint8_t* st = smem + s * kStageBytes;
-        split_tile<32 * kXfWarps>(st, st + kA32, st + kA32 + kA16, BM, t, a_scale);
+        uint8_t* dst = ring_b + sb * kOpBytes;
+        split_tile<32 * kXfWarps>(ring_a + sa * kA32, dst, dst + kA16, BM, t, a_scale);
         tma::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+        if (lane == 0) {
+          tma::mbar_arrive(&bars->xf[sb]);
+          tma::mbar_arrive(&bars->empty_a[sa]);
+        }
         if constexpr (PROF) pc[5] += clock64() - t_w0;
+        if (++sa == kAStages) { sa = 0; pa ^= 1u; }
+        if (++sb == kBStages) { sb = 0; pb ^= 1u; }
       }
     }
   } else {
@@ -441,15 +491,23 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
 // 32-feature groups and SBO = 512 B between 8-sample atoms; one K=16 MMA step spans two atoms (1024 B).
 // Grid = ngroups x 2 output tiles (128 rows of dW) x sample chunks; fp32 atomics into dW.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kWgStages = 2;
+// Two rings, as in the forward kernel: fp32 landing tiles (dZ 16 KB + H 32 KB per k-block of 32 samples) three deep,
+// freed as soon as the transform has read them, and ONE fp16 operand slot (dZ hi | lo, H hi | lo: 48 KB) that transform
+// and MMA take turns on.  The first version kept both in one 96 KB stage, two deep: a stage was held for load latency +
+// transform + MMA and the period was (3000 + 500 + 768) / 2 clk per k-block.
+constexpr int kWgLand = 3;
 constexpr int kWgA32 = 128 * BK * 4, kWgA16 = 128 * BK * 2;  // 16 KB / 8 KB
 constexpr int kWgB32 = 256 * BK * 4, kWgB16 = 256 * BK * 2;  // 32 KB / 16 KB (sized for IN = 256)
-constexpr int kWgStageBytes = kWgA32 + 2 * kWgA16 + kWgB32 + 2 * kWgB16;  // 96 KB
+constexpr int kWgLandBytes = kWgA32 + kWgB32;                // 48 KB
+constexpr int kWgOpBytes = 2 * kWgA16 + 2 * kWgB16;          // 48 KB
+constexpr int kWgRingBytes = kWgLand * kWgLandBytes + kWgOpBytes;  // 192 KB
 constexpr int kWgXfWarps = 8;
 constexpr int kWgThreads = 32 * (2 + 4 + kWgXfWarps);
 
 struct WgBarriers {
-  uint64_t full[kWgStages], xf[kWgStages], empty[kWgStages], tmem_full;
+  uint64_t full[kWgLand], empty[kWgLand];  // landing ring: TMA tx bytes / transform warps done reading
+  uint64_t xf, op_free;                    // operand slot: written by the transform / its MMAs have completed
+  uint64_t tmem_full;
   uint32_t tmem_base, pad_;
 };
 
@@ -464,7 +522,8 @@ struct WgradParams {
 __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  WgBarriers* bars = reinterpret_cast<WgBarriers*>(smem + kWgStages * kWgStageBytes);
+  uint8_t* op = smem + kWgLand * kWgLandBytes;  // dZ hi | dZ lo | H hi | H lo
+  WgBarriers* bars = reinterpret_cast<WgBarriers*>(smem + kWgRingBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.x % P.ngroups;
   const int rest = blockIdx.x / P.ngroups;
@@ -474,16 +533,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
   const int kb0 = chunk * P.kb_per_chunk;
   const int kb1 = (kb0 + P.kb_per_chunk < n_kb_total) ? kb0 + P.kb_per_chunk : n_kb_total;
   const int n_kb = kb1 - kb0;
-  const int gB = IN / 32;
   const uint32_t b32_bytes = (uint32_t)IN * BK * 4;
   const uint32_t tmem_cols = IN <= 32 ? 32u : (IN <= 64 ? 64u : (IN <= 128 ? 128u : 256u));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < kWgLand; ++s) {
       tma::mbar_init(&bars->full[s], 1);
-      tma::mbar_init(&bars->xf[s], kWgXfWarps);
-      tma::mbar_init(&bars->empty[s], 1);
+      tma::mbar_init(&bars->empty[s], kWgXfWarps);
     }
+    tma::mbar_init(&bars->xf, kWgXfWarps);
+    tma::mbar_init(&bars->op_free, 1);
     tma::mbar_init(&bars->tmem_full, 1);
     tma::fence_barrier_init();
   }
@@ -500,44 +559,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
 
   if (n_kb > 0) {
     if (warp == 0) {
-      const int n_box = 4 + gB;
-      int pf = (P.flags >> 8) & 0xff;
-      pf = pf == 0 ? 3 : (pf == 255 ? 0 : pf);
-      if (lane < n_box)
-        for (int j = 0; j < pf && j < n_kb; ++j) {
-          if (lane < 4) tma::prefetch_2d(&P.z[grp], out_tile * 128 + lane * 32, (kb0 + j) * BK);
-          else tma::prefetch_2d(&P.h[grp], (lane - 4) * 32, (kb0 + j) * BK);
-        }
-      for (int it = 0; it < n_kb; ++it) {
-        if (lane < n_box && it + pf < n_kb) {
-          if (lane < 4) tma::prefetch_2d(&P.z[grp], out_tile * 128 + lane * 32, (kb0 + it + pf) * BK);
-          else tma::prefetch_2d(&P.h[grp], (lane - 4) * 32, (kb0 + it + pf) * BK);
-        }
-        const int s = it % kWgStages;
-        const uint32_t ph = (it / kWgStages) & 1u;
-        if (lane == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < n_kb; ++it) {
+          const int s = it % kWgLand;
+          const uint32_t ph = (it / kWgLand) & 1u;
           tma::mbar_wait(&bars->empty[s], ph ^ 1u);
           tma::mbar_arrive_expect_tx(&bars->full[s], kWgA32 + b32_bytes);
-        }
-        __syncwarp();
-        if (lane < n_box) {
-          uint8_t* st = smem + s * kWgStageBytes;
+          uint8_t* st = smem + s * kWgLandBytes;
           const int m0 = (kb0 + it) * BK;  // samples >= n are zero-filled
-          if (lane < 4) tma::load_2d(st + lane * 4096, &P.z[grp], out_tile * 128 + lane * 32, m0, &bars->full[s]);
-          else tma::load_2d(st + kWgA32 + 2 * kWgA16 + (lane - 4) * 4096, &P.h[grp], (lane - 4) * 32, m0, &bars->full[s]);
+          // ONE box per operand: [32 samples x 128 floats] of dZ (this CTA's half of the output rows), [32 x IN] of H
+          tma::load_2d(st, &P.z[grp], out_tile * 128, m0, &bars->full[s]);
+          tma::load_2d(st + kWgA32, &P.h[grp], 0, m0, &bars->full[s]);
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = idesc_f16(128, IN, 1, 1);
         for (int it = 0; it < n_kb; ++it) {
-          const int s = it % kWgStages;
-          const uint32_t ph = (it / kWgStages) & 1u;
-          tma::mbar_wait(&bars->xf[s], ph);  // implies full[s]
+          tma::mbar_wait(&bars->xf, (uint32_t)it & 1u);  // the operand slot holds k-block `it`
           fence_after_sync();
-          const uint32_t sa = tma::smem_u32(smem + s * kWgStageBytes);
-          const uint32_t sb = sa + kWgA32 + 2 * kWgA16 + kWgB32;
-          const uint64_t a_hi = desc_mn_sw64(sa + kWgA32, 2048), a_lo = desc_mn_sw64(sa + kWgA32 + kWgA16, 2048);
+          const uint32_t sa = tma::smem_u32(op);
+          const uint32_t sb = sa + 2 * kWgA16;
+          const uint64_t a_hi = desc_mn_sw64(sa, 2048), a_lo = desc_mn_sw64(sa + kWgA16, 2048);
           const uint64_t b_hi = desc_mn_sw64(sb, 2048), b_lo = desc_mn_sw64(sb + kWgB16, 2048);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -547,7 +590,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
             mma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
             mma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
           }
-          mma_commit(&bars->empty[s]);
+          mma_commit(&bars->op_free);
         }
         mma_commit(&bars->tmem_full);
       }
@@ -573,18 +616,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
     } else {
       const int t = threadIdx.x - 6 * 32;
       for (int it = 0; it < n_kb; ++it) {
-        const int s = it % kWgStages;
-        const uint32_t ph = (it / kWgStages) & 1u;
-        tma::mbar_wait(&bars->full[s], ph);
-        uint8_t* st = smem + s * kWgStageBytes;
-        uint8_t* b32 = st + kWgA32 + 2 * kWgA16;
-        // groups of [32 samples x 32 floats] (4 KB) -> [32 samples x 32 halfs] (2 KB); consecutive groups are contiguous
-        // on both sides, so "rows" simply runs over groups * 32
-        split_tile<32 * kWgXfWarps>(st, st + kWgA32, st + kWgA32 + kWgA16, 4 * 32, t, z_scale);
-        split_tile<32 * kWgXfWarps>(b32, b32 + kWgB32, b32 + kWgB32 + kWgB16, gB * 32, t, 1.0f);
+        const int s = it % kWgLand;
+        const uint32_t ph = (it / kWgLand) & 1u;
+        tma::mbar_wait(&bars->full[s], ph);                       // the fp32 tiles have landed
+        tma::mbar_wait(&bars->op_free, ((uint32_t)it & 1u) ^ 1u);  // the MMAs of k-block it-1 have read the operand slot
+        uint8_t* st = smem + s * kWgLandBytes;
+        uint8_t* b32 = st + kWgA32;
+        split_rows_plain<32 * kWgXfWarps>(st, 128, op, op + kWgA16, t, z_scale);
+        split_rows_plain<32 * kWgXfWarps>(b32, IN, op + 2 * kWgA16, op + 2 * kWgA16 + kWgB16, t, 1.0f);
         tma::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&bars->xf[s]);
+        if (lane == 0) {
+          tma::mbar_arrive(&bars->xf);
+          tma::mbar_arrive(&bars->empty[s]);
+        }
       }
     }
   }
@@ -596,27 +641,52 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
   }
 }
 
-// ---- weights -> fp16 (hi, lo) of w * 2^kWeightScaleLog2, all hidden matrices of the policy in ONE launch ----------------
+// ---- weights -> packed fp16 (hi, lo) tiles of w * 2^kWeightScaleLog2, all hidden matrices of the policy in ONE launch ----
 struct SplitJob {
-  const float* src;
-  __half* hi;
-  __half* lo;
-  int64_t n;
+  const float* src;   // [256 out, K in]
+  uint8_t* fwd;       // forward pack
+  uint8_t* dgrad;     // dgrad pack or NULL
+  int K;
 };
 struct SplitJobs {
   SplitJob j[8];
   int count;
 };
+// item = (out row o, 8 consecutive inputs): 16 bytes of hi and of lo in each pack
 __global__ void __launch_bounds__(256) split_half_kernel(SplitJobs jobs) {
   const float scale = (float)(1 << kWeightScaleLog2);
   for (int q = 0; q < jobs.count; ++q) {
     const SplitJob& J = jobs.j[q];
+    const int cpr = J.K / 8;  // 16-byte chunks per row
+    const int64_t items = (int64_t)BN * cpr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < J.n; i += stride) {
-      const float x = J.src[i] * scale;
-      const __half h = __float2half_rn(x);
-      J.hi[i] = h;
-      J.lo[i] = __float2half_rn(x - __half2float(h));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+      const int o = (int)(i / cpr), c8 = (int)(i - (int64_t)o * cpr);  // inputs [8*c8, 8*c8+8)
+      const float4 x0 = *reinterpret_cast<const float4*>(J.src + (size_t)o * J.K + 8 * c8);
+      const float4 x1 = *reinterpret_cast<const float4*>(J.src + (size_t)o * J.K + 8 * c8 + 4);
+      const float v[8] = {x0.x * scale, x0.y * scale, x0.z * scale, x0.w * scale,
+                          x1.x * scale, x1.y * scale, x1.z * scale, x1.w * scale};
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      {  // forward pack: k-block = 8*c8 / 32, tile row o (64 B), chunk (c8 & 3) swizzled by ((o >> 1) & 3)
+        const int kb = c8 >> 2, ch = c8 & 3;
+        uint8_t* d = J.fwd + (size_t)kb * (2 * kB16) + o * 64 + ((ch ^ ((o >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + kB16) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      if (J.dgrad != nullptr) {  // dgrad pack: k-block = o / 32, group = input / 64, row o % 32 (128 B), chunk swizzled by (row & 7)
+        const int kb = o >> 5, r = o & 31, grp = c8 >> 3, ch = c8 & 7;
+        uint8_t* d = J.dgrad + (size_t)kb * (2 * kB16) + grp * 4096 + r * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + kB16) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
   }
 }
@@ -642,23 +712,16 @@ int launch(const GemmLaunch* L, int ngroups, int64_t M, int K, int epi, int b_mn
   for (int g = 0; g < ngroups; ++g) {
     const GemmLaunch& l = L[g];
     const uintptr_t al = reinterpret_cast<uintptr_t>(l.a) | reinterpret_cast<uintptr_t>(l.b_hi) |
-                         reinterpret_cast<uintptr_t>(l.b_lo) | reinterpret_cast<uintptr_t>(l.c) |
-                         reinterpret_cast<uintptr_t>(l.h);
+                         reinterpret_cast<uintptr_t>(l.c) | reinterpret_cast<uintptr_t>(l.h);
     if (al & 15) return RB200_E_ALIGN;
     int e = encode_f32_sw128(&P.a[g], l.a, (uint64_t)M, (uint64_t)K, BM);
-    if (!b_mn) {  // weights [256 out, K in] fp16, box {32 k, 256 rows}, SWIZZLE_64B
-      if (!e) e = encode_f16(&P.bh[g], l.b_hi, BN, (uint64_t)K, 32, BN, 64);
-      if (!e) e = encode_f16(&P.bl[g], l.b_lo, BN, (uint64_t)K, 32, BN, 64);
-    } else {      // weights [256 out = K rows, 256 in = N cols] fp16, box {64 in, 32 out}, SWIZZLE_128B
-      if (!e) e = encode_f16(&P.bh[g], l.b_hi, BN, BN, 64, 32, 128);
-      if (!e) e = encode_f16(&P.bl[g], l.b_lo, BN, BN, 64, 32, 128);
-    }
+    P.wpack[g] = reinterpret_cast<const uint8_t*>(l.b_hi);
     if (!e) e = encode_f32_sw128(&P.c[g], l.c, (uint64_t)M, BN, 32);
     if (e) return RB200_E_UNSUPPORTED;
     P.g[g] = Group{l.bias, l.h, l.colsum, l.amax_in, l.amax_out};
   }
   static bool attr_done = false;
-  constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
+  constexpr int kSmem = kRingBytes + kStagingBytes + 1024 + (int)sizeof(Barriers);
   static_assert(kSmem <= 232448, "tc_h_gemm_kernel shared memory");
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_h_gemm_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -693,14 +756,14 @@ int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st)
     const uintptr_t al = reinterpret_cast<uintptr_t>(L[g].z) | reinterpret_cast<uintptr_t>(L[g].h) |
                          reinterpret_cast<uintptr_t>(L[g].dW);
     if (al & 15) return RB200_E_ALIGN;
-    int e = encode_f32_sw128(&P.z[g], L[g].z, (uint64_t)n, 256, 32);
-    if (!e) e = encode_f32_sw128(&P.h[g], L[g].h, (uint64_t)n, (uint64_t)IN, 32);
+    int e = rb::encode_tmap_2d(&P.z[g], L[g].z, 4, (uint64_t)n, 256, 32, 128);           // box [32 samples x 128 floats]
+    if (!e) e = rb::encode_tmap_2d(&P.h[g], L[g].h, 4, (uint64_t)n, (uint64_t)IN, 32, (uint32_t)IN);  // [32 x IN]
     if (e) return RB200_E_UNSUPPORTED;
     P.dW[g] = L[g].dW;
     P.amax_z[g] = L[g].amax_z;
   }
   static bool attr_done = false;
-  constexpr int kSmem = kWgStages * kWgStageBytes + 1024 + (int)sizeof(WgBarriers);
+  constexpr int kSmem = kWgRingBytes + 1024 + (int)sizeof(WgBarriers);
   static_assert(kSmem <= 232448, "tc_h_wgrad_kernel shared memory");
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(tc_h_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -724,9 +787,10 @@ int split_weights(const SplitSpec* specs, int count, cudaStream_t st) {
   jobs.count = count;
   int64_t total = 0;
   for (int i = 0; i < count; ++i) {
-    jobs.j[i] = SplitJob{specs[i].src, reinterpret_cast<__half*>(specs[i].hi), reinterpret_cast<__half*>(specs[i].lo),
-                         specs[i].n};
-    total = specs[i].n > total ? specs[i].n : total;
+    const int64_t K = specs[i].n / BN;
+    if (K * BN != specs[i].n || K % BK != 0 || (specs[i].lo != nullptr && K != BN)) return RB200_E_SHAPE;
+    jobs.j[i] = SplitJob{specs[i].src, reinterpret_cast<uint8_t*>(specs[i].hi), reinterpret_cast<uint8_t*>(specs[i].lo), (int)K};
+    total = specs[i].n / 8 > total ? specs[i].n / 8 : total;
   }
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)rb::sm_count() * 4;
@@ -757,11 +821,13 @@ extern "C" int rb200_tc_gemm_h(const float* A, const float* B, float* C, int64_t
   if (M <= 0 || K <= 0 || K % rb::tc::BK != 0) return RB200_E_SHAPE;
   cudaStream_t st = rb::as_stream(stream);
   const int64_t nb = (int64_t)rb::tc::BN * K;
-  rb::tch::SplitSpec sp{B, work, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + nb * 2), nb};
+  if (mode && K != rb::tc::BN) return RB200_E_SHAPE;
+  // forward pack always; the dgrad pack (square matrices only) behind it
+  rb::tch::SplitSpec sp{B, work, mode ? work + nb : nullptr, nb};
   int e = rb::tch::split_weights(&sp, 1, st);
   if (e) return e;
   rb::tch::GemmLaunch l{};
-  l.a = A; l.b_hi = sp.hi; l.b_lo = sp.lo; l.c = C; l.amax_in = amax;
+  l.a = A; l.b_hi = mode ? sp.lo : sp.hi; l.b_lo = nullptr; l.c = C; l.amax_in = amax;
   return rb::tch::launch(&l, 1, M, K, rb::tc::EPI_STORE, mode ? 1 : 0, st);
 }
 

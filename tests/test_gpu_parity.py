@@ -314,9 +314,14 @@ def test_mlp_forward_backward_adamw_golden(golden):
     torch.testing.assert_close(out["values"].cpu(), _t(g["pol_values"]), rtol=RTOL, atol=1e-5)
     pol.flat_grads.zero_()
     pol.backward(_t(g["pol_wl"]).cuda(), _t(g["pol_wv"]).cuda(), _t(g["pol_we"]).cuda())
+    worst = 0.0
     for n, gr in pol.named_grads():
         ref = _t(g["pol_g_" + n])
-        torch.testing.assert_close(gr.cpu(), ref, rtol=1e-3, atol=1e-5 * max(1.0, ref.abs().max().item()), msg=n)
+        # parameter gradients are sums over samples with cancellation: the bar is 1e-4 relative per element plus 1e-5 of
+        # the tensor's own scale (round 1 used rtol 1e-3; measured max |diff| / max |ref| is printed)
+        torch.testing.assert_close(gr.cpu(), ref, rtol=RTOL, atol=1e-5 * max(1.0, ref.abs().max().item()), msg=n)
+        worst = max(worst, ((gr.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+    print(f"max |dW - ref| / max |ref| over parameter tensors: {worst:.2e}")
     # optimiser: 3 steps with the reference's own gradients
     for n, gr in pol.named_grads():
         gr.copy_(_t(g["pol_g_" + n]))
@@ -352,9 +357,12 @@ def test_mlp_config2_shapes_vs_oracle():
     ((o["logprobs"] * wl).sum() + (o["values"] * wv).sum()).backward()
     pol.flat_grads.zero_()
     pol.backward(wl.cuda(), wv.cuda(), None)
+    worst = 0.0
     for name, gr in pol.named_grads():
         ref = params[name].grad
-        torch.testing.assert_close(gr.cpu(), ref, rtol=1e-3, atol=2e-5 * max(ref.abs().max().item(), 1e-6), msg=name)
+        torch.testing.assert_close(gr.cpu(), ref, rtol=RTOL, atol=2e-5 * max(ref.abs().max().item(), 1e-6), msg=name)
+        worst = max(worst, ((gr.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+    print(f"config-2 shapes: max |dW - ref| / max |ref| over parameter tensors: {worst:.2e}")
 
 
 def test_mlp_sample_given_noise_vs_oracle():
