@@ -163,39 +163,6 @@ __device__ __forceinline__ void split_tile(const uint8_t* __restrict__ src, uint
   }
 }
 
-// fp32 PLAIN row-major landing tile [32 samples x `cols` floats] (one TMA box per operand: 32 row requests of
-// 4*cols bytes instead of cols/32 boxes of 32 x 128 B) -> the same fp16 hi / lo groups split_tile produces:
-// [cols/32 groups][32 samples x 32 halfs] SWIZZLE_64B.  item = (sample r, 8 consecutive floats p): consecutive threads
-// read consecutive 32-byte pieces of a row (conflict-free LDS.128).
-template <int NT>
-__device__ __forceinline__ void split_rows_plain(const uint8_t* __restrict__ src, int cols, uint8_t* __restrict__ hi,
-                                                 uint8_t* __restrict__ lo, int t, float scale) {
-  const int ppr = cols >> 3;  // 8-float pieces per row
-  const int items = 32 * ppr;
-#pragma unroll 2
-  for (int i = t; i < items; i += NT) {
-    const int r = i / ppr, pc = i - r * ppr;
-    const uint8_t* sp = src + ((size_t)r * cols + pc * 8) * 4;
-    const float4 x0 = *reinterpret_cast<const float4*>(sp);
-    const float4 x1 = *reinterpret_cast<const float4*>(sp + 16);
-    const float v[8] = {x0.x * scale, x0.y * scale, x0.z * scale, x0.w * scale,
-                        x1.x * scale, x1.y * scale, x1.z * scale, x1.w * scale};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-      h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    const int g = pc >> 2, cp = pc & 3;  // feature group of 32, 16-byte chunk inside its 64-byte row
-    const int doff = (g * 32 + r) * 64 + ((cp ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(hi + doff) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + doff) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
-}
-
 // PROF instantiations (tools/gemm_role_probe.py): cycles each role of CTA 0 spends waiting / working
 template <bool PROF>
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long& acc) {
@@ -559,17 +526,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
 
   if (n_kb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        for (int it = 0; it < n_kb; ++it) {
-          const int s = it % kWgLand;
-          const uint32_t ph = (it / kWgLand) & 1u;
+      // boxes {32 floats, 32 samples} with SWIZZLE_128B, one lane per box (a single plain [32 x 128|IN] box per operand
+      // was tried: 64 row requests instead of 384 per k-block, but the unswizzled landing tile costs more in the
+      // transform than the requests save: 191 vs 163 us, profiles/r02_tc_h_unit_timings.txt)
+      const int gB = IN / 32;
+      const int n_box = 4 + gB;
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % kWgLand;
+        const uint32_t ph = (it / kWgLand) & 1u;
+        if (lane == 0) {
           tma::mbar_wait(&bars->empty[s], ph ^ 1u);
           tma::mbar_arrive_expect_tx(&bars->full[s], kWgA32 + b32_bytes);
+        }
+        __syncwarp();
+        if (lane < n_box) {
           uint8_t* st = smem + s * kWgLandBytes;
           const int m0 = (kb0 + it) * BK;  // samples >= n are zero-filled
-          // ONE box per operand: [32 samples x 128 floats] of dZ (this CTA's half of the output rows), [32 x IN] of H
-          tma::load_2d(st, &P.z[grp], out_tile * 128, m0, &bars->full[s]);
-          tma::load_2d(st + kWgA32, &P.h[grp], 0, m0, &bars->full[s]);
+          if (lane < 4) tma::load_2d(st + lane * 4096, &P.z[grp], out_tile * 128 + lane * 32, m0, &bars->full[s]);
+          else tma::load_2d(st + kWgA32 + (lane - 4) * 4096, &P.h[grp], (lane - 4) * 32, m0, &bars->full[s]);
         }
       }
     } else if (warp == 1) {
@@ -622,8 +596,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
         tma::mbar_wait(&bars->op_free, ((uint32_t)it & 1u) ^ 1u);  // the MMAs of k-block it-1 have read the operand slot
         uint8_t* st = smem + s * kWgLandBytes;
         uint8_t* b32 = st + kWgA32;
-        split_rows_plain<32 * kWgXfWarps>(st, 128, op, op + kWgA16, t, z_scale);
-        split_rows_plain<32 * kWgXfWarps>(b32, IN, op + 2 * kWgA16, op + 2 * kWgA16 + kWgB16, t, 1.0f);
+        // groups of [32 samples x 32 floats] (4 KB) -> [32 samples x 32 halfs] (2 KB); consecutive groups are contiguous
+        // on both sides, so "rows" simply runs over groups * 32
+        split_tile<32 * kWgXfWarps>(st, op, op + kWgA16, 4 * 32, t, z_scale);
+        split_tile<32 * kWgXfWarps>(b32, op + 2 * kWgA16, op + 2 * kWgA16 + kWgB16, (IN / 32) * 32, t, 1.0f);
         tma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -756,8 +732,8 @@ int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st)
     const uintptr_t al = reinterpret_cast<uintptr_t>(L[g].z) | reinterpret_cast<uintptr_t>(L[g].h) |
                          reinterpret_cast<uintptr_t>(L[g].dW);
     if (al & 15) return RB200_E_ALIGN;
-    int e = rb::encode_tmap_2d(&P.z[g], L[g].z, 4, (uint64_t)n, 256, 32, 128);           // box [32 samples x 128 floats]
-    if (!e) e = rb::encode_tmap_2d(&P.h[g], L[g].h, 4, (uint64_t)n, (uint64_t)IN, 32, (uint32_t)IN);  // [32 x IN]
+    int e = encode_f32_sw128(&P.z[g], L[g].z, (uint64_t)n, 256, 32);
+    if (!e) e = encode_f32_sw128(&P.h[g], L[g].h, (uint64_t)n, (uint64_t)IN, 32);
     if (e) return RB200_E_UNSUPPORTED;
     P.dW[g] = L[g].dW;
     P.amax_z[g] = L[g].amax_z;
