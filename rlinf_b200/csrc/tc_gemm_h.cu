@@ -33,13 +33,16 @@ using rb::tc::BN;
 // (~700) + MMA (768), i.e. ~1500 clk per k-block against 768 of MMA (tools/gemm_role_probe.py).  Now the fp32 landing
 // tiles have their own deep ring (freed as soon as the transform has read them: 6 x 16 KB of activations in flight per
 // SM) and the MMA operands (A hi | lo written by the transform, weight hi | lo landed by TMA) a shallow one.
-constexpr int kAStages = 6;         // fp32 landing ring of the streamed operand
-constexpr int kBStages = 2;         // fp16 operand ring
+constexpr int kAStages = 4;         // fp32 landing ring of the streamed operand
+constexpr int kBStages = 2;         // fp16 A hi | lo slots (written by the transform)
+constexpr int kWStages = 3;         // weight tile ring (one 32 KB bulk copy each): with two slots the MMA waited ~650 clk
+                                    // per k-block for the weight tile (32 KB over L2 -> SM take ~2000 clk to arrive)
 constexpr int kA32 = BM * BK * 4;   // 16 KB fp32 landing tile of the streamed operand
 constexpr int kA16 = BM * BK * 2;   //  8 KB per fp16 half
 constexpr int kB16 = BN * BK * 2;   // 16 KB per fp16 half of the weight tile
-constexpr int kOpBytes = 2 * kA16 + 2 * kB16;               // 48 KB: A hi | A lo | W hi | W lo
-constexpr int kRingBytes = kAStages * kA32 + kBStages * kOpBytes;  // 192 KB
+constexpr int kOpBytes = 2 * kA16;  // 16 KB: A hi | A lo
+constexpr int kWBytes = 2 * kB16;   // 32 KB: W hi | W lo
+constexpr int kRingBytes = kAStages * kA32 + kBStages * kOpBytes + kWStages * kWBytes;  // 64 + 32 + 96 = 192 KB
 constexpr int kXfWarpsDefault = 4;  // transform warps per CTA: template parameter XF of the forward / dgrad kernel (4 or 8)
 constexpr int kEpiWarps = 8;  // two per TMEM lane quarter, 128 of the 256 output columns each: the bias+tanh / (1-h^2)
                               // epilogue of one warp per scheduler took 7.8 k cycles per tile against 6.1 k of MMA
@@ -178,9 +181,10 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long lo
 struct __align__(16) Barriers {
   uint64_t full_a[kAStages];   // fp32 landing tile arrived (TMA tx bytes)
   uint64_t empty_a[kAStages];  // transform warps have read it
-  uint64_t full_b[kBStages];   // weight halves arrived (TMA tx bytes)
   uint64_t xf[kBStages];       // transform warps have written A hi | lo
-  uint64_t empty_b[kBStages];  // MMAs reading the operand slot have completed (tcgen05.commit)
+  uint64_t empty_b[kBStages];  // MMAs reading the A slot have completed (tcgen05.commit)
+  uint64_t full_w[kWStages];   // weight tile arrived (bulk-copy tx bytes)
+  uint64_t empty_w[kWStages];  // MMAs reading the weight slot have completed (tcgen05.commit)
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -217,7 +221,8 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring_a = smem;                       // kAStages x [128 rows x 32 fp32] SWIZZLE_128B
-  uint8_t* ring_b = smem + kAStages * kA32;     // kBStages x (A hi | A lo | W hi | W lo)
+  uint8_t* ring_w = smem + kAStages * kA32;                 // kWStages x (W hi | W lo), 1024-aligned (MN-major SWIZZLE_128B)
+  uint8_t* ring_b = ring_w + kWStages * kWBytes;            // kBStages x (A hi | A lo)
   uint8_t* staging = smem + kRingBytes;
   Barriers* bars = reinterpret_cast<Barriers*>(staging + kStagingBytes);
 
@@ -234,9 +239,12 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
       tma::mbar_init(&bars->empty_a[s], kXfWarps);
     }
     for (int s = 0; s < kBStages; ++s) {
-      tma::mbar_init(&bars->full_b[s], 1);
       tma::mbar_init(&bars->xf[s], kXfWarps);
       tma::mbar_init(&bars->empty_b[s], 1);
+    }
+    for (int s = 0; s < kWStages; ++s) {
+      tma::mbar_init(&bars->full_w[s], 1);
+      tma::mbar_init(&bars->empty_w[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       tma::mbar_init(&bars->tmem_full[b], 1);
@@ -276,13 +284,12 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
           ++ja;
           if (++sa == kAStages) { sa = 0; pa ^= 1u; }
         }
-        if (jb < total && tma::mbar_try_wait(&bars->empty_b[sb], pb ^ 1u)) {
+        if (jb < total && tma::mbar_try_wait(&bars->empty_w[sb], pb ^ 1u)) {
           const int kb = (int)(jb % n_kb);
-          uint8_t* wdst = ring_b + sb * kOpBytes + 2 * kA16;
-          tma::mbar_arrive_expect_tx(&bars->full_b[sb], 2 * kB16);
-          bulk_load(wdst, P.wpack[grp] + (size_t)kb * (2 * kB16), 2 * kB16, &bars->full_b[sb]);  // hi | lo, one copy
+          tma::mbar_arrive_expect_tx(&bars->full_w[sb], kWBytes);
+          bulk_load(ring_w + sb * kWBytes, P.wpack[grp] + (size_t)kb * kWBytes, kWBytes, &bars->full_w[sb]);  // hi | lo
           ++jb;
-          if (++sb == kBStages) { sb = 0; pb ^= 1u; }
+          if (++sb == kWStages) { sb = 0; pb ^= 1u; }
         }
       }
     }
@@ -300,12 +307,14 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           const int s = it % kBStages;
           const uint32_t ph = (it / kBStages) & 1u;
-          wait_bar<PROF>(&bars->full_b[s], ph, pc[2]);
+          const int sw = it % kWStages;
+          const uint32_t phw = (it / kWStages) & 1u;
+          wait_bar<PROF>(&bars->full_w[sw], phw, pc[2]);
           wait_bar<PROF>(&bars->xf[s], ph, pc[3]);
           fence_after_sync();
           const uint32_t sa32 = tma::smem_u32(ring_b + s * kOpBytes);
           const uint64_t a_hi = desc_k_sw64(sa32), a_lo = desc_k_sw64(sa32 + kA16);
-          const uint32_t sbase = sa32 + 2 * kA16;
+          const uint32_t sbase = tma::smem_u32(ring_w + sw * kWBytes);
           const uint64_t b_hi = P.b_mn ? desc_mn_sw128(sbase, 4096) : desc_k_sw64(sbase);
           const uint64_t b_lo = P.b_mn ? desc_mn_sw128(sbase + kB16, 4096) : desc_k_sw64(sbase + kB16);
 #pragma unroll
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(threads_for(kXfWarps), 1) tc_h_gemm_kernel(con
             mma_f16(d_tmem, a_hi + ka, b_hi + kbo, idesc, 1u);
           }
           mma_commit(&bars->empty_b[s]);
+          mma_commit(&bars->empty_w[sw]);
         }
         mma_commit(&bars->tmem_full[buf]);
       }
@@ -468,7 +478,7 @@ constexpr int kWgB32 = 256 * BK * 4, kWgB16 = 256 * BK * 2;  // 32 KB / 16 KB (s
 constexpr int kWgLandBytes = kWgA32 + kWgB32;                // 48 KB
 constexpr int kWgOpBytes = 2 * kWgA16 + 2 * kWgB16;          // 48 KB
 constexpr int kWgRingBytes = kWgLand * kWgLandBytes + kWgOpBytes;  // 192 KB
-constexpr int kWgXfWarps = 8;
+constexpr int kWgXfWarps = 16;  // four per scheduler: the fp32 -> fp16 split of 48 KB per k-block took 1025 clk with 8 (tools/gemm_role_probe.py)
 constexpr int kWgThreads = 32 * (2 + 4 + kWgXfWarps);
 
 struct WgBarriers {
@@ -484,9 +494,13 @@ struct WgradParams {
   const float* amax_z[2];  // max|dZ| per group (or NULL)
   int64_t n;
   int IN, kb_per_chunk, ngroups, flags;
+  long long* prof;  // [16] (PROF instantiation: slots 9..15)
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = PROF ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* op = smem + kWgLand * kWgLandBytes;  // dZ hi | dZ lo | H hi | H lo
@@ -535,7 +549,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
         const int s = it % kWgLand;
         const uint32_t ph = (it / kWgLand) & 1u;
         if (lane == 0) {
-          tma::mbar_wait(&bars->empty[s], ph ^ 1u);
+          wait_bar<PROF>(&bars->empty[s], ph ^ 1u, pc[0]);
           tma::mbar_arrive_expect_tx(&bars->full[s], kWgA32 + b32_bytes);
         }
         __syncwarp();
@@ -550,7 +564,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
       if (lane == 0) {
         const uint32_t idesc = idesc_f16(128, IN, 1, 1);
         for (int it = 0; it < n_kb; ++it) {
-          tma::mbar_wait(&bars->xf, (uint32_t)it & 1u);  // the operand slot holds k-block `it`
+          wait_bar<PROF>(&bars->xf, (uint32_t)it & 1u, pc[1]);  // the operand slot holds k-block `it`
           fence_after_sync();
           const uint32_t sa = tma::smem_u32(op);
           const uint32_t sb = sa + 2 * kWgA16;
@@ -592,8 +606,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
       for (int it = 0; it < n_kb; ++it) {
         const int s = it % kWgLand;
         const uint32_t ph = (it / kWgLand) & 1u;
-        tma::mbar_wait(&bars->full[s], ph);                       // the fp32 tiles have landed
-        tma::mbar_wait(&bars->op_free, ((uint32_t)it & 1u) ^ 1u);  // the MMAs of k-block it-1 have read the operand slot
+        wait_bar<PROF>(&bars->full[s], ph, pc[2]);                       // the fp32 tiles have landed
+        wait_bar<PROF>(&bars->op_free, ((uint32_t)it & 1u) ^ 1u, pc[3]);  // the MMAs of k-block it-1 have read the operand slot
+        const long long t_w0 = PROF ? clock64() : 0;
         uint8_t* st = smem + s * kWgLandBytes;
         uint8_t* b32 = st + kWgA32;
         // groups of [32 samples x 32 floats] (4 KB) -> [32 samples x 32 halfs] (2 KB); consecutive groups are contiguous
@@ -606,6 +621,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_h_wgrad_kernel(const __grid_
           tma::mbar_arrive(&bars->xf);
           tma::mbar_arrive(&bars->empty[s]);
         }
+        if constexpr (PROF) pc[4] += clock64() - t_w0;
+      }
+    }
+  }
+  if constexpr (PROF) {
+    if (blockIdx.x == 0 && P.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 6)) {
+      for (int i = 0; i < 5; ++i)
+        if (pc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(P.prof + 9 + i), (unsigned long long)pc[i]);
+      if (warp == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(P.prof + 14), (unsigned long long)(clock64() - t_start));
+        atomicAdd(reinterpret_cast<unsigned long long*>(P.prof + 15), (unsigned long long)n_kb);
       }
     }
   }
@@ -742,7 +768,9 @@ int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st)
   constexpr int kSmem = kWgRingBytes + 1024 + (int)sizeof(WgBarriers);
   static_assert(kSmem <= 232448, "tc_h_wgrad_kernel shared memory");
   if (!attr_done) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_h_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t ce = cudaFuncSetAttribute(tc_h_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_h_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (ce != cudaSuccess) return (int)ce;
     attr_done = true;
   }
@@ -751,7 +779,9 @@ int wgrad(const WgradLaunch* L, int ngroups, int64_t n, int IN, cudaStream_t st)
   if (chunks < 1) chunks = 1;
   if (chunks > n_kb) chunks = n_kb;
   P.kb_per_chunk = (n_kb + chunks - 1) / chunks;
-  tc_h_wgrad_kernel<<<ngroups * 2 * chunks, kWgThreads, kSmem, st>>>(P);
+  P.prof = g_prof;
+  if (g_prof) tc_h_wgrad_kernel<true><<<ngroups * 2 * chunks, kWgThreads, kSmem, st>>>(P);
+  else tc_h_wgrad_kernel<false><<<ngroups * 2 * chunks, kWgThreads, kSmem, st>>>(P);
   rb::count_launch();
   cudaError_t ce = cudaPeekAtLastError();
   return ce == cudaSuccess ? 0 : (int)ce;

@@ -34,3 +34,27 @@ for M in (262144, 32768):
             else:
                 print(f"M={M} mode={mode} production {us:.1f} us (incl. split kernel)", flush=True)
 lib.rb200_tc_h_debug(None)
+
+# ---- wgrad: slots 9..15 = producer-wait-empty, mma-wait-xf, xf-wait-full, xf-wait-op_free, xf-work, total, k-blocks ----
+WNAMES = ["prod_wait_empty", "mma_wait_xf", "xf_wait_full", "xf_wait_op_free", "xf_work", "total", "k_blocks"]
+for n in (262144, 32768):
+    Z = torch.randn(n, 256, device="cuda") / 64
+    H = torch.tanh(torch.randn(n, 256, device="cuda"))
+    dW = torch.zeros(256, 256, device="cuda")
+    for use_prof in (True, False):
+        lib.rb200_tc_h_debug(C.c_void_p(prof.data_ptr()) if use_prof else None)
+        for _ in range(2):
+            L.check(lib.rb200_tc_wgrad_h(L.ptr(Z), L.ptr(H), L.ptr(dW), n, 256, None, L.stream_ptr()), "w")
+        torch.cuda.synchronize()
+        prof.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.rb200_tc_wgrad_h(L.ptr(Z), L.ptr(H), L.ptr(dW), n, 256, None, L.stream_ptr()), "w")
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3
+        if use_prof:
+            c = prof.tolist()[9:16]
+            print(f"wgrad n={n} PROF {us:.1f} us; CTA0 cycles: " + " ".join(f"{a}={b}" for a, b in zip(WNAMES, c)), flush=True)
+        else:
+            print(f"wgrad n={n} production {us:.1f} us", flush=True)
+lib.rb200_tc_h_debug(None)
