@@ -458,6 +458,9 @@ def _update_phase_bytes(n, obs, act, H):
 
 
 def run_ours(a):
+    # ONE JSON line on stdout: anything a library prints at the C level (NCCL's "NCCL version ..." line) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -644,7 +647,8 @@ def run_ours(a):
                                     "sample": f"1 iteration of {n_envs} of {a.B} envs x T={a.T}, same update structure; "
                                               f"oracle port of the reference CPU path, torch {cores} threads",
                                     "seconds": mean_s, "phases_s": phases}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -96,6 +96,10 @@ class EmbodiedActor:
         # on B200: bit-for-bit the same kernels; measured gain 48.4 -> 45.2 ms per update at 32 k samples / step - the
         # step is kernel-bound, so this is a few percent, not the 40 % the round-1 notes expected)
         self._graph_update = self.cfg.actor.get("cuda_graph_update", False)  # True / False / "auto"
+        # Multi-rank graphed steps are EXPERIMENTAL and off unless actor.cuda_graph_multi_rank is set: on 2 x B200
+        # (torch 2.11 / NCCL 2.28.9) the 2-rank parity test with the NCCL all-reduce captured inside the step graph never
+        # completed (pytest timeout after 500 s, profiles/r02_two_rank_nccl.txt); the eager all-reduce path passes.
+        self._graph_multi_rank = bool(self.cfg.actor.get("cuda_graph_multi_rank", False))
         self._capture_nccl = bool(self.cfg.actor.get("cuda_graph_capture_nccl", True))
         self._static_batch: dict = {}
         self._step_graphs: dict = {}
@@ -180,6 +184,8 @@ class EmbodiedActor:
         use_graph = self._graph_update
         if use_graph == "auto":  # small per-rank mini-batches: the step is short enough for launch gaps to matter
             use_graph = batch_size_per_rank <= 65536
+        if self._world_size > 1 and not self._graph_multi_rank:
+            use_graph = False
         graphed = bool(use_graph) and self._train_calls > 0  # the first call runs eagerly (lazy initialisation)
         self._train_calls += 1
         if graphed:

@@ -29,7 +29,7 @@ def main():
     n = B * T
     cfg = synthetic_ppo_config(B=B, T=T, obs_dim=obs, action_dim=act, update_epoch=2, num_minibatches=2,
                                micro_batch_size=n // 2 // world // 2, world_size=1,
-                               **{"actor.cuda_graph_update": graph})
+                               **{"actor.cuda_graph_update": graph, "actor.cuda_graph_multi_rank": graph})
     run = EmbodiedRunner(cfg)
     assert run.B == B // world
     out = {"rank": rank, "ok": True, "iters": []}
