@@ -299,10 +299,13 @@ def run_reference(a):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r01_ncu_mlp_step_v3_table.txt, profiles/r01_ncu_gae_v4_summary.txt); only valid at the captured shape.
 NCU_TRAFFIC = {
-    # profiles/r02_ncu_tc_h_kernels.txt: grouped (two-tower) launches at 262144 rows; per tower = half
-    ("tc_gemm_fwd", 262144): (537.5e6 + 483.3e6) / 2,   # 268.8 MB read + 241.6 MB written back before the kernel ends
-    ("tc_wgrad", 262144): (1075.3e6 + 4.4e6) / 2,
+    # profiles/r02_ncu_final_table.txt (ncu --set full, per launch; GEMMs: grouped two-tower launches at 262144 rows, per tower = half)
+    ("tc_gemm_fwd", 262144): (537.4e6 + 484.0e6) / 2,   # 268.7 MB read + 242.0 MB written back before the kernel ends
+    ("tc_wgrad", 262144): (1074.6e6 + 4.5e6) / 2,
     ("gae_scan", 512, 4096): 18.9e6,    # reads only: the 16.8 MB of results are still in L2 when the kernel ends
+    ("ppo", 262144): 64.4e6 + 3.0e6,    # 2x the algorithmic 32.5 MB: every gathered 4-byte scalar pulls a 32-byte sector
+    ("logits_fwd", 4096, 32000): 524.6e6 + 3.7e6,
+    ("logits_bwd", 4096, 32000): 524.5e6 + 478.7e6,
 }
 
 
@@ -379,7 +382,8 @@ def kernel_rooflines(a, peaks, torch):
 
     t = time_graph(ppo_all, rot)
     out["gather_ppo_loss_fwd_bwd"] = {"bound": "hbm", "achieved": bytes_ppo / t / 1e9, "peak": peaks["hbm_gbs"],
-                                      "unit": "GB/s", "frac": bytes_ppo / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                      "unit": "GB/s", "frac": bytes_ppo / t / 1e9 / peaks["hbm_gbs"],
+                                      "traffic": NCU_TRAFFIC.get(("ppo", mb)),
                                       "us_per_launch": t * 1e6, "algorithmic_bytes": bytes_ppo,
                                       "launch_note": "ONE kernel (the last CTA finalises and clears the workspace); rollout rows gathered "
                                                      "through idx: each gathered 4-byte scalar pulls a 32-byte sector"}
@@ -406,7 +410,9 @@ def kernel_rooflines(a, peaks, torch):
     for key, fn, nbytes in (("logits_logprob_entropy_fwd", lg_fwd, Nl * V * 4), ("logits_logprob_entropy_bwd", lg_bwd, 2 * Nl * V * 4)):
         t = time_graph(fn, 1)
         out[key] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": nbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": t * 1e6,
+                    "frac": nbytes / t / 1e9 / peaks["hbm_gbs"],
+                    "traffic": NCU_TRAFFIC.get(("logits_fwd" if key.endswith("fwd") else "logits_bwd", Nl, V)),
+                    "us_per_launch": t * 1e6,
                     "algorithmic_bytes": nbytes, "rows": Nl, "vocab": V}
     del lg, dlg
 
