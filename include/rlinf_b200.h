@@ -330,9 +330,11 @@ int rb200_tc_gemm_h(const float* A, const float* B, float* C, int64_t M, int K, 
 int rb200_tc_wgrad_h(const float* Z, const float* H, float* dW, int64_t n, int IN, const float* amax,
                      rb200_stream_t stream);
 
-/* Experiment switches of the tensor-core kernels (tools/ only; default 0): bit 0 = additionally mask the streamed operand's
- * hi part in shared memory (not needed: the tensor core truncates), bit 1 = fused-rollout variants with a 4-k-step weight
- * prefetch (experimental), bit 2 = cta_group::2 (CTA-pair) forward/dgrad GEMM (experimental), bits 8-15 = TMA L2-prefetch distance in k-blocks (255 = off). */
+/* Experiment switches (tools/ and tests only; default 0 = the shipped kernels): 1 = additionally mask the streamed operand's
+ * hi part in shared memory in the 3xTF32 kernels (not needed: the tensor core truncates), 2 = round-1 layers in the fp32
+ * SIMT fused rollout (one-k-step weight prefetch), 8 = round-1 3xTF32 GEMMs instead of the fp16-split ones, 32 = one
+ * fp16-split GEMM launch per tower instead of the grouped launch, 64 = 8 transform warps in the fp16-split forward kernel,
+ * bits 8-15 = TMA L2-prefetch distance of the 3xTF32 kernels in k-blocks (255 = off). */
 int rb200_debug_set_flags(int flags);
 /* probe hook of the fp16-split GEMM (csrc/tc_gemm_h.cu): 16 int64 per-role wait / work cycle counters of CTA 0 */
 int rb200_tc_h_debug(void* prof16);

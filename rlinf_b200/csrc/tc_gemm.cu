@@ -550,7 +550,6 @@ int launch(const float* a, const float* b_hi, const float* b_lo, const Params& p
                        reinterpret_cast<uintptr_t>(b_lo) | reinterpret_cast<uintptr_t>(p.c) |
                        reinterpret_cast<uintptr_t>(p.h);
   if (al & 15) return RB200_E_ALIGN;
-  if (g_debug_flags & 4) return launch_pair(a, b_hi, b_lo, p, st);  // experimental cta_group::2 kernel
   CUtensorMap ta, tb_hi, tb_lo, tc;
   int e = encode_sw128(&ta, a, (uint64_t)p.M, (uint64_t)p.K, BM);
   if (!e) e = encode_sw128(&tb_hi, b_hi, BN, (uint64_t)p.K, BN);

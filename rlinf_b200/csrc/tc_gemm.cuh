@@ -21,15 +21,15 @@ struct Params {
 };
 
 // debug/experiment switches (rb200_debug_set_flags): bit 0 = also mask the streamed operand's hi part in shared memory
-// (default off: the tensor core ignores the low 13 mantissa bits of a kind::tf32 operand - verified bit-identical), bit 1 = fused rollout kernel
-// with deeper weight prefetch (experimental), bit 2 = cta_group::2 forward/dgrad GEMM (experimental), bits 8.. = L2 prefetch distance in k-blocks (0 = default)
+// (default off: the tensor core ignores the low 13 mantissa bits of a kind::tf32 operand - verified bit-identical), bit 1 (2) = round-1
+// fused-rollout layers (one-k-step weight prefetch), bit 3 (8) = round-1 3xTF32 GEMMs instead of the fp16-split kernels, bit 5 (32) = one
+// fp16-split GEMM launch per tower, bit 6 (64) = 8 transform warps in the fp16-split forward kernel, bits 8-15 = TF32 kernels' L2
+// prefetch distance in k-blocks (0 = default)
 extern int g_debug_flags;
 
 // C[M,256] = epi( A[M,K] . (B_hi+B_lo)[256,K]^T ).  A is plain fp32 (split into exact-TF32 hi/lo inside the kernel);
 // B is a pre-split weight matrix (rb::tc::split).  All pointers 16-byte aligned.
 int launch(const float* a, const float* b_hi, const float* b_lo, const Params& p, cudaStream_t st);
-// experimental cta_group::2 variant (tc_gemm2.cu), used by launch() when g_debug_flags bit 2 is set
-int launch_pair(const float* a, const float* b_hi, const float* b_lo, const Params& p, cudaStream_t st);
 // dW[256, IN] += Z[n,256]^T . H[n,IN]   (IN % 32 == 0, <= 256), plain fp32 operands, fp32 atomics into dW
 int wgrad(const float* z, const float* h, float* dW, int64_t n, int IN, cudaStream_t st);
 // x -> (hi, lo) exact-TF32 pair, hi + lo ~= x to 2^-21 relative; hi may alias x.

@@ -47,31 +47,6 @@ def test_tc_wgrad_matches_fp64(n, IN):
     assert err <= (5e-6 + 2e-7 * n ** 0.5) * scale + 2e-6, (err, scale)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RB200_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernel variants (rb200_debug_set_flags): RB200_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("M,K", [(256, 32), (128, 256), (1000, 128), (5000, 256), (262144, 256)])
-def test_experimental_cta_pair_gemm_bit_identical(M, K):
-    """cta_group::2 variant (debug flag bit 2, tc_gemm2.cu): same products, same k order -> same bits."""
-    from rlinf_b200 import _lib as L
-
-    lib = L.load()
-    g = torch.Generator(device="cuda").manual_seed(M + K)
-    A = torch.randn(M, K, device="cuda", generator=g)
-    B = torch.randn(256, K, device="cuda", generator=g) / K ** 0.5
-    work = torch.empty(512 * K, device="cuda")
-    outs = []
-    try:
-        for flags in (0, 4):
-            lib.rb200_debug_set_flags(flags)
-            C = torch.full((M, 256), float("nan"), device="cuda")
-            L.check(lib.rb200_tc_gemm(L.ptr(A), L.ptr(B), L.ptr(C), M, K, L.ptr(work), L.stream_ptr()), "tc_gemm")
-            torch.cuda.synchronize()
-            outs.append(C)
-    finally:
-        lib.rb200_debug_set_flags(0)
-    assert torch.equal(outs[0], outs[1])
-
-
 # ---- round 2: fp16-split kind::f16 kernels (csrc/tc_gemm_h.cu) ------------------------------------------------------------
 def _amax(t):
     return t.abs().max().reshape(1).to(torch.float32)
