@@ -21,6 +21,35 @@ import torch
 from . import rl_oracle as O
 
 
+def bootstrap_rewards(rewards, dones, truncations, bootstrap_values, gamma, bootstrap_type="standard", auto_reset=True):
+    """EnvWorker.compute_bootstrap_rewards (rlinf/workers/env/env_worker.py:719-758) for env rewards only (no reward
+    model): rewards [B, C] are returned untouched without bootstrap values or without auto_reset; else
+    r[:, -1] += gamma * V(final_obs) where the chunk's LAST sub-step is truncated ("standard") or done (any other type).
+    Pinned against the reference function body itself (tests/golden/make_golden_r4.py)."""
+    adj = rewards.clone()
+    if bootstrap_values is None or not auto_reset or dones is None:
+        return adj
+    flag = (truncations if bootstrap_type == "standard" else dones)[:, -1]
+    if not bool(flag.any()):
+        return adj
+    fv = torch.zeros_like(adj[:, -1], dtype=torch.float32)
+    fv[flag] = bootstrap_values[flag].reshape(-1).to(torch.float32)
+    adj[:, -1] += gamma * fv
+    return adj
+
+
+def chunk_flags(raw_terminations, raw_truncations):
+    """Flag aggregation of env.chunk_step (rlinf/envs/maniskill/maniskill_env.py:355-369): raw per-sub-step flags [B, C]
+    are any-reduced over the chunk and reported on its last sub-step only.  Returns (terminations, truncations, past_dones)."""
+    past_term = raw_terminations.any(dim=1)
+    past_trunc = raw_truncations.any(dim=1)
+    chunk_term = torch.zeros_like(raw_terminations)
+    chunk_trunc = torch.zeros_like(raw_truncations)
+    chunk_term[:, -1] = past_term
+    chunk_trunc[:, -1] = past_trunc
+    return chunk_term, chunk_trunc, past_term | past_trunc
+
+
 class SyntheticEnvCPU:
     """Same dynamics as rlinf_b200.envs.SyntheticVectorEnv (same W_s/W_a from the same seed); own RNG."""
 
@@ -89,18 +118,12 @@ class SyntheticEnvCPU:
             terms.append(t)
             truncs.append(tr)
         rewards = torch.stack(rewards, dim=1)
-        past_term = torch.stack(terms, dim=1).any(dim=1)
-        past_trunc = torch.stack(truncs, dim=1).any(dim=1)
-        past_done = past_term | past_trunc
+        chunk_term, chunk_trunc, past_done = chunk_flags(torch.stack(terms, dim=1), torch.stack(truncs, dim=1))
         final = state
         nxt = state
         if self.auto_reset:
             nxt = torch.where(past_done.unsqueeze(-1), noise[:, C * (obs + 2):], state)
             self.elapsed[past_done] = 0
-        chunk_term = torch.zeros(B, C, dtype=torch.bool)
-        chunk_trunc = torch.zeros(B, C, dtype=torch.bool)
-        chunk_term[:, -1] = past_term
-        chunk_trunc[:, -1] = past_trunc
         self.state = nxt
         return ([{"states": nxt}], rewards, chunk_term, chunk_trunc, [{"final_observation": {"states": final}}])
 
@@ -186,12 +209,8 @@ class RunnerOracle:
             if final_obs is not None:  # get_bootstrap_values: second forward on final_obs
                 boot = O.mlp_forward(self.params, final_obs["states"], None, want_entropy=False)["values"][:, :1]
             if rewards is not None:  # compute_bootstrap_rewards
-                adj = rewards.clone()
-                flag = (dones if boot_always else trunc)[:, -1]
-                if boot is not None and self.env.auto_reset and bool(flag.any()):
-                    fv = torch.zeros_like(adj[:, -1])
-                    fv[flag] = boot[flag].reshape(-1)
-                    adj[:, -1] += gamma * fv
+                adj = bootstrap_rewards(rewards, dones, trunc, boot, gamma, "always" if boot_always else "standard",
+                                        self.env.auto_reset)
                 lists["rewards"].append(adj.contiguous())
             lists["dones"].append(dones.contiguous())
             lists["terminations"].append(term.contiguous())
