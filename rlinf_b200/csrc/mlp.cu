@@ -4,11 +4,12 @@
 // ValueHead, rlinf/models/embodiment/modules/value_head.py:18-67 (3x256 tanh MLP -> value_dim, last layer
 // without bias); backward = what autograd derives from them.
 //
-// Hidden-layer GEMMs run on the tensor cores (tc_gemm.cu: tcgen05 kind::tf32 with 3xTF32 compensation, fp32-level
-// accuracy) whenever the operand shapes allow TMA (K % 32 == 0, no row gather); the fp32 SIMT GEMM (sgemm.cuh)
-// covers the remaining shapes.  Activations and activation-gradients are stored once, as plain fp32 [n,256]
-// (6 tanh outputs per forward, tanh' = 1 - h^2); the tensor-core kernels split them into exact-TF32 (hi, lo) pairs
-// on the fly in shared memory.
+// Hidden-layer GEMMs run on the tensor cores whenever the operand shapes allow TMA (K % 32 == 0, no row gather): by
+// default the fp16-split kernels (tc_gemm_h.cu: tcgen05 kind::f16, a = a_hi + a_lo in fp16, three MMAs per product,
+// fp32-level accuracy, both towers per launch), with debug flag 8 the round-1 3xTF32 kernels (tc_gemm.cu); the fp32 SIMT
+// GEMM (sgemm.cuh) covers the remaining shapes.  Activations and activation-gradients are stored once, as plain fp32
+// [n,256] (6 tanh outputs per forward, tanh' = 1 - h^2); the tensor-core kernels split them into (hi, lo) pairs on the
+// fly in shared memory.
 // The heads (256 -> act mean, 256 -> value) are fused with the Normal log-prob / entropy epilogue and their backward.
 #include <curand_kernel.h>
 
@@ -644,8 +645,9 @@ TowerWH tower_wh(const rb200_mlp_layout* L, const float* ws, bool value) {
 }
 }  // namespace
 
-// Refresh the exact-TF32 (hi, lo) weight copies the tensor-core GEMMs read. Call after every parameter update
-// (once per optimiser step / once per rollout); 2 x 10 tiny kernels.
+// Refresh the weight copies the tensor-core GEMMs read: packed fp16 (hi, lo) tiles in ONE launch (default), or the
+// exact-TF32 (hi, lo) copies of the round-1 kernels (debug flag 8; 2 x 10 tiny kernels). Call after every parameter update
+// (once per optimiser step / once per rollout).
 extern "C" int rb200_mlp_prepare_weights(const rb200_mlp_layout* L, const float* params, float* wsplit,
                                          rb200_stream_t stream) {
   int e = check_layout(L);

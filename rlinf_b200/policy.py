@@ -39,7 +39,7 @@ class MLPPolicy:
         self.flat_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._spec = self._build_spec()
         self._scratch: dict[tuple, torch.Tensor] = {}
-        # tensor-core operand cache (exact-TF32 hi/lo copies of the hidden-layer weights)
+        # tensor-core operand cache (packed fp16 hi/lo tiles of the hidden-layer weights; TF32 copies with debug flag 8)
         self.use_tensor_cores = True
         self.wsplit = torch.zeros(int(lib.rb200_mlp_wsplit_floats(C.byref(self.layout))), dtype=torch.float32,
                                   device=self.device)
