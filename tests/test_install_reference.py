@@ -89,3 +89,20 @@ def test_reference_dispatchers_reach_the_cuda_callables(installed):
     for loss_type in ("actor_critic", "actor", "decoupled_actor_critic"):
         with pytest.raises(Rb200Error):
             ref.registry.policy_loss(**dict(loss_kw, loss_type=loss_type))
+
+
+def test_logits_wrappers_are_signature_compatible_with_the_reference():
+    """SURVEY 8(f)3 drop-ins: rlinf_b200.ops.compute_logprobs_from_logits / compute_entropy_from_logits take the reference's
+    positional and keyword arguments (rlinf/utils/utils.py:454-512) and, without a GPU, refuse to compute on the host."""
+    ref = ref_loader.load_reference()
+    from rlinf_b200 import ops
+    from rlinf_b200._lib import Rb200Error
+
+    for name in ("compute_logprobs_from_logits", "compute_entropy_from_logits"):
+        want = list(inspect.signature(getattr(ref.utils, name)).parameters)
+        got = list(inspect.signature(getattr(ops, name)).parameters)
+        assert got == want, (name, got, want)
+    if not torch.cuda.is_available():
+        logits, target = torch.randn(2, 3, 11), torch.randint(0, 11, (2, 3))
+        with pytest.raises((Rb200Error, RuntimeError, AssertionError, OSError)):
+            ops.compute_logprobs_from_logits(logits, target, op_type="torch")
