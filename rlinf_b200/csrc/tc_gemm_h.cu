@@ -5,8 +5,9 @@
 //   * kind::f16 issues at twice the kind::tf32 rate, so an fp32-accurate product costs peak/3 instead of peak/6;
 //   * operands are 2 bytes in shared memory: the three MMAs re-read 72 KB per 128x256x32 k-block instead of 147 KB and
 //     the weight tiles TMA-fill 32 KB instead of 64 KB (round 1 was bound by exactly this shared-memory traffic);
-//   * the weight matrix is read K-major for the forward GEMM and MN-major for dgrad FROM THE SAME fp16 copy (UMMA
-//     descriptors select the major-ness), so the transposed weight copies and their 8 refresh kernels are gone;
+//   * the weights are packed per k-block as pre-swizzled fp16 (hi | lo) tiles - a K-major forward pack and an MN-major dgrad
+//     pack per matrix, written by one pack kernel - and fetched with ONE 32 KB bulk copy per k-block; the transposed fp32
+//     weight copies of round 1 and their 8 refresh kernels are gone;
 //   * one launch serves BOTH towers (policy backbone + value MLP have identical shapes): grouped tile scheduling halves
 //     the launches and fills the tail wave of small per-rank batches.
 // Activations / activation gradients stay plain fp32 in HBM (one copy); the streamed operand is TMA-landed as fp32
