@@ -838,6 +838,34 @@ def build_adamw(params: dict, lr, value_lr, betas=(0.9, 0.999), eps=1e-8, weight
     return torch.optim.AdamW(groups, eps=eps, weight_decay=weight_decay)
 
 
+def prime_optimizer_state(optimizer):
+    """warmup_optimizer_state (rlinf/utils/utils.py:594-663), the last call of build_optimizer
+    (fsdp_model_manager.py:589): one step with every lr set to 0 over the CURRENT .grad tensors (zeros where .grad is
+    None), then lr restored and every `step` counter reset to 0.  Parameters do not move (lr = 0 also disables the
+    decoupled decay), but the moments do absorb whatever gradient is present: (1-b1) g and (1-b2) g^2.  At construction
+    time there are no gradients and this is a no-op; when the optimiser is rebuilt at the end of critic warm-up the
+    value-head parameters still carry the clipped gradient of the last warm-up step (golden_r5 "warmup")."""
+    saved_lr = [g["lr"] for g in optimizer.param_groups]
+    saved_grad = {}
+    for g in optimizer.param_groups:
+        g["lr"] = 0.0
+        for p in g["params"]:
+            saved_grad[p] = p.grad
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+    with torch.no_grad():
+        optimizer.step()
+    for g, lr in zip(optimizer.param_groups, saved_lr):
+        g["lr"] = lr
+    for p, gr in saved_grad.items():
+        p.grad = gr
+        st = optimizer.state.get(p, {})
+        if torch.is_tensor(st.get("step")):
+            st["step"].zero_()
+        elif "step" in st:
+            st["step"] = 0
+
+
 def lr_lambda(optim_cfg: dict, base_lr: float):
     """build_lr_scheduler + get_lr_scheduler (fsdp_model_manager.py:465-499, fsdp/utils.py:522-604): the LambdaLR
     multiplier as a function of the scheduler step (constant / cosine / openpi_cosine)."""

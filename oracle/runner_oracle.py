@@ -167,9 +167,11 @@ class RunnerOracle:
 
     def _build_optimizer(self, warmup):
         o = self.cfg["actor"]["optim"]
-        return O.build_adamw(self.params, o["lr"], o.get("value_lr", o["lr"]),
-                             (o.get("adam_beta1", 0.9), o.get("adam_beta2", 0.999)), o.get("adam_eps", 1e-8),
-                             o.get("weight_decay", 1e-2), enable_critic_warmup=warmup)
+        opt = O.build_adamw(self.params, o["lr"], o.get("value_lr", o["lr"]),
+                            (o.get("adam_beta1", 0.9), o.get("adam_beta2", 0.999)), o.get("adam_eps", 1e-8),
+                            o.get("weight_decay", 1e-2), enable_critic_warmup=warmup)
+        O.prime_optimizer_state(opt)  # build_optimizer's closing warmup_optimizer_state call
+        return opt
 
     def _optimizer_step(self):
         """FSDPModelManager.optimizer_step (fsdp_model_manager.py:429-463)."""
@@ -239,6 +241,9 @@ class RunnerOracle:
             batch = O.merge_rollout_epochs(batch, E)
         if not cfg["env"]["train"]["auto_reset"] and not cfg["env"]["train"].get("ignore_terminations", False):
             batch["loss_mask"], batch["loss_mask_sum"] = O.loss_mask_from_dones(batch["dones"])
+        if a.get("filter_rewards", False):  # embodied_fsdp_actor_worker.py:236-282
+            batch["loss_mask"] = O.reward_filter_mask(batch["rewards"], batch.get("loss_mask"), a["group_size"],
+                                                      a["rewards_lower_bound"], a["rewards_upper_bound"])
         res = O.adv_and_returns_embodied(a["adv_type"], batch["rewards"], batch["dones"], batch.get("prev_values"),
                                          batch.get("loss_mask"), batch.get("loss_mask_sum"), a.get("gamma", 1),
                                          a.get("gae_lambda", 1), a.get("group_size", 8), a["reward_type"])

@@ -342,7 +342,7 @@ class EmbodiedActor:
             if self.optimizer_steps >= self.critic_warmup_steps:
                 self.critic_warmup_steps = 0
                 self._set_frozen_groups()
-                self.optimizer.reset_state()
+                self.optimizer.reset_state(carry_grads=True)
                 self.lr_schedule = LRSchedule(self.cfg.actor.optim, base_lr=self.cfg.actor.optim.lr)
                 self.optimizer.lr_scale = self.lr_schedule.multiplier()
             return lr_list

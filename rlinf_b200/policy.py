@@ -275,14 +275,30 @@ class FlatAdamW:
                                          L.ptr(self.exp_avg_sq), n, self._ends, L.ptr(self._lr_dev), len(self._kinds),
                                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.clip_grad,
                                          float(grad_scale), L.ptr(self.grad_sq), L.ptr(self.state), st), "adamw_step")
+        self._last_grad_scale = float(grad_scale)
         p.mark_params_changed()
 
-    def reset_state(self):
+    def reset_state(self, carry_grads: bool = False):
         """Fresh moments and step count: the reference REBUILDS its optimiser when critic warm-up ends
-        (fsdp_model_manager.py:452-459)."""
-        self.exp_avg.zero_()
-        self.exp_avg_sq.zero_()
+        (fsdp_model_manager.py:452-459).
+
+        `carry_grads`: build_optimizer finishes with warmup_optimizer_state (rlinf/utils/utils.py:594-663) - one lr = 0
+        step over the CURRENT `.grad` tensors (zeros only where `.grad` is None) followed by a step-count reset.  At
+        the end of critic warm-up the value-head parameters still hold the clipped gradient g of the last warm-up step
+        (zero_grad only runs at the start of the next global batch), so the rebuilt optimiser starts from
+        exp_avg = (1-b1) g, exp_avg_sq = (1-b2) g^2 there and from zeros for the actor (grad None while frozen; the
+        flat buffer holds exact zeros for it).  Pinned by tests/golden/golden_r5.npz case "warmup"."""
         self.state[0].zero_()
+        if not carry_grads:
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            return
+        # what clip_grad_norm_ left in .grad: (1/world_size average) x clip coefficient, rounded like the step kernel
+        gmul = self.state[2].to(torch.float32) * getattr(self, "_last_grad_scale", 1.0)
+        g = self.policy.flat_grads * gmul
+        g = torch.where(self.state[3] != 0, torch.zeros_like(g), g)  # skipped (non-finite) step: plain zeros
+        torch.mul(g, 1.0 - self.betas[0], out=self.exp_avg)
+        torch.mul(g * g, 1.0 - self.betas[1], out=self.exp_avg_sq)
 
     def last_grad_norm(self) -> torch.Tensor:
         """0-dim device tensor (read it on the host once per run_training, not per step)."""

@@ -309,7 +309,9 @@ def test_runner_update_vs_oracle_at_config2_network_shapes():
 # ---------------------------------------------------------------------------------------------------------------
 def test_critic_warmup_matches_reference_optimizer_semantics():
     """critic_warmup_steps=3 with 4 optimiser steps per run_training: actor frozen (no update, no decay) for 3 steps,
-    lr reported 0.0, then a REBUILT optimiser (fresh moments / step count) - fsdp_model_manager.py:451-459."""
+    lr reported 0.0, then a REBUILT optimiser (step count 0; moments primed by warmup_optimizer_state with the last
+    warm-up gradient of the value head, zeros for the actor) - fsdp_model_manager.py:451-459, utils/utils.py:594-663;
+    the oracle side of this comparison is pinned against the reference worker by golden_r5 "warmup"."""
     from rlinf_b200.config import synthetic_ppo_config
     from rlinf_b200.runner import EmbodiedRunner
 
